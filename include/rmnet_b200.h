@@ -1,0 +1,183 @@
+/*
+ * rmnet_b200.h -- C ABI of librmnet_b200.so: the B200 (sm_100a) implementation of hzxie/RMNet's
+ * per-frame regional memory-read hot path.
+ *
+ * This is the drop-in boundary.  The reference has no C ABI of its own for this path: its
+ * boundary is pybind11 (extensions/reg_att_map_generator/reg_att_map_generator_cuda.cpp:36-38),
+ * the CPython C-API (extensions/flow_affine_transformation/flow_affine_transformation.cpp:87-99)
+ * and plain Python methods (models/rmnet.py).  Each entry point below cites the reference
+ * interface it replaces; INTEGRATION.md shows the reference-side binding (ctypes stubs that keep
+ * the reference's Python signatures).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / pybind types.
+ *   - every `const T* x` / `T* x` is a DEVICE pointer unless the parameter name ends in `_host`.
+ *   - the caller owns all memory (inputs, outputs, workspaces, banks); the library never allocates
+ *     device memory and keeps no pointer past the call.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no implicit host sync
+ *     (exception: the *_host convenience entry points, which synchronise `stream` before returning).
+ *   - return 0 on success, a negative RMNET_E_* code otherwise; rmnet_last_error() returns a
+ *     thread-local message.  Functions are re-entrant; there is no global mutable state.
+ *   - float tensors are float32, C-contiguous unless a stride parameter says otherwise.
+ */
+#ifndef RMNET_B200_H_
+#define RMNET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define RMNET_API __attribute__((visibility("default")))
+#else
+#define RMNET_API
+#endif
+
+#define RMNET_ABI_VERSION 1
+
+#define RMNET_OK 0
+#define RMNET_E_INVALID (-1)   /* bad argument (null pointer, non-positive size, misaligned, unsupported shape) */
+#define RMNET_E_CUDA (-2)      /* a CUDA runtime / driver call failed; see rmnet_last_error() */
+#define RMNET_E_WORKSPACE (-3) /* workspace or bank too small */
+#define RMNET_E_UNSUPPORTED (-4)
+
+/* Channel counts fixed by the reference architecture (models/rmnet.py:185-186: keydim=128, valdim=512). */
+#define RMNET_CK 128
+#define RMNET_CV 512
+
+/* precision modes of the memory read (see DESIGN.md "precision") */
+#define RMNET_PREC_SPLIT3 0 /* strict: 16-bit hi/lo split operands, 3 tensor-core products per GEMM, fp32 accumulate */
+#define RMNET_PREC_SINGLE 1 /* fast:   hi planes only, 1 product per GEMM                                            */
+/* kernel selection (both are sm_100a CUDA; there is no CPU fallback) */
+#define RMNET_IMPL_AUTO 0
+#define RMNET_IMPL_SIMT 1   /* CUDA-core fp32 FFMA flash kernel (cross-check / odd shapes) */
+#define RMNET_IMPL_UMMA 2   /* tcgen05 + TMEM + TMA kernel                                  */
+
+RMNET_API int rmnet_abi_version(void);
+RMNET_API const char *rmnet_last_error(void);
+/* Number of kernels this thread has launched through the library since the last reset (bench.py's gpu_launches). */
+RMNET_API long long rmnet_launch_count(void);
+RMNET_API void rmnet_launch_count_reset(void);
+/* 1 when the tcgen05 / TMEM / TMA memory-read kernel is compiled into this build, else 0. */
+RMNET_API int rmnet_has_umma(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Regional attention-map generator.
+ * Replaces reg_att_map_generator.forward(mask, prob_threshold, n_pts_threshold, n_bbox_loose_pixels)
+ *   (reg_att_map_generator_cuda.cpp:26-38 -> reg_att_map_generator.cu:95-123, kernel :15-93).
+ *   mask     [B,K,H,W] f32
+ *   bboxes   [B,K,4]   i32 = (x_min, x_max, y_min, y_max) inclusive; channel 0 -> (0,0,0,0)
+ *   att_full [B,K,H,W] f32 in {0,1}, nullable (every element is written: no pre-zeroing needed)
+ *   workspace: rmnet_reg_att_map_workspace_bytes(B,K) bytes, ZERO-FILLED ONCE by the caller at
+ *              allocation; the kernels leave it zeroed again (self-cleaning), so it can be reused
+ *              by consecutive calls on the same stream.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API size_t rmnet_reg_att_map_workspace_bytes(int B, int K);
+RMNET_API int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,
+                              int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes,
+                              float *att_full, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RMNet.warp(img0, flow) -> (img1, mask)                       (models/rmnet.py:252-278)
+ *   img0 [B,C,H,W], flow [B,2,H,W] (ch 0 = x, ch 1 = y, pixels); img1 [B,C,H,W]; valid [B,C,H,W]
+ *   (the reference's `mask` output: the same [H,W] validity plane broadcast over C), nullable.
+ *   Bit-exact with the reference evaluated on torch's CUDA backend (reciprocal-multiply
+ *   normalisation, FMA-chained bilinear taps, >= 0.9999 validity).
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, float *img1,
+                       float *valid, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * RMNet.get_att_map(prev_mask, flow) fused: warp + threshold + bbox in ONE pass, the warped mask
+ * is never written to HBM.                                      (models/rmnet.py:280-287)
+ *   outputs / workspace as rmnet_reg_att_map_forward.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
+                               float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels,
+                               int *bboxes, float *att_full, void *workspace, size_t workspace_bytes,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Low-resolution cell rectangles: the closed form of
+ *   F.interpolate(pad(att_map), scale_factor=1/16)             (models/rmnet.py:245, :307+:356)
+ * for a rectangular att_map:  cx in [ceil((x0+pad_l)/16), floor((x1+pad_l)/16)], same for y.
+ *   bboxes [count,4] i32 (x_min,x_max,y_min,y_max) -> rects [count,4] i32 (cx0,cx1,cy0,cy1),
+ *   clamped to the h x w grid; empty when lo > hi.  `skip_channel0_every` = K marks every K-th
+ *   entry (the background channel, whose att_map is all zero) as empty; pass 0 to disable.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_cell_rects_from_bboxes(const int *bboxes, int count, int pad_l, int pad_t, int h, int w,
+                                 int skip_channel0_every, int *rects, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Memory bank: the preallocated, region-compacted replacement of the reference's growing
+ * `keys [B,K,128,T,h,w]` / `values [B,K,512,T,h,w]` tensors (models/rmnet.py:239-248 pad_memory +
+ * regional multiply, :416-426 torch.cat growth, :348-349 per-object gather).
+ *
+ * One opaque device blob per clip; slot s holds object s+1.  Only in-region cells are stored
+ * (16-bit hi/lo planes, keys position-major, values channel-major); masked cells are only counted.
+ * A frame is first written as the TEMPORARY last frame (the reference's `this_keys`); `commit != 0`
+ * makes it permanent (`keys = this_keys`, :424-426).  The next memorize overwrites a temporary frame.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API size_t rmnet_bank_bytes(int n_slots, int cap_cells);
+RMNET_API int rmnet_bank_reset(void *bank, size_t bank_bytes, int n_slots, int cap_cells, void *stream);
+/*   k4 [n_obj,128,h*w] (object stride k_obj_stride, channel stride k_ch_stride, in floats),
+ *   v4 [n_obj,512,h*w] likewise; rects [n_obj,4] cell rectangles of this frame (device);
+ *   elem_format: 0 = bf16 planes, 1 = fp16 planes. */
+RMNET_API int rmnet_bank_memorize(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *k4,
+                        long long k_obj_stride, long long k_ch_stride, const float *v4,
+                        long long v_obj_stride, long long v_ch_stride, const int *rects, int n_obj,
+                        int h, int w, int elem_format, int commit, void *stream);
+/* Host-visible copy of the per-slot counters (synchronises `stream`): out_host [n_slots,8] i32 =
+ * (cells_committed, cells_temp, zeros_committed, zeros_temp, frames_committed, frames_temp, 0, 0). */
+RMNET_API int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells, int *out_host, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Regional memory read against a bank: replaces the per-frame
+ *   F.interpolate(att,1/16); k4e*=att; v4e*=att; MemoryReader.forward(key, value, k4e, v4e)
+ *   (models/rmnet.py:355-361, :147-165) for all objects in one call.
+ *   q_key [n_q?,128,h*w], q_val [.,512,h*w]: q_obj_stride = 0 when one query frame is shared by all
+ *     objects (the reference's expand, :332-333), else the per-object stride in floats.
+ *   q_rects [n_obj,4] cell rectangles of the query frame (device); NULL = dense (all cells).
+ *   mem_val [n_obj,1024,h,w] f32: channels 0..511 the memory read, 512..1023 the (masked) q_val.
+ *   workspace: rmnet_memory_read_workspace_bytes(...) bytes (partial results of the split-KV pass).
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells);
+RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells,
+                           const float *q_key, const float *q_val, long long q_obj_stride,
+                           const int *q_rects, int n_obj, int h, int w, int elem_format,
+                           int precision, int impl, float *mem_val, void *workspace,
+                           size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Literal MemoryReader.forward(m_key, m_val, q_key, q_val) -> mem_val   (models/rmnet.py:147-165)
+ *   m_key [n,128,T,h,w], m_val [n,512,T,h,w], q_key [n,128,h,w], q_val [n,512,h,w] (contiguous f32)
+ *   mem_val [n,1024,h,w].  Region-agnostic (dense): packs the inputs into a scratch bank inside
+ *   `workspace` and runs the same read kernel.  workspace >= rmnet_memory_reader_workspace_bytes().
+ *   The reference's second output `p [n,T*h*w,h*w]` is produced only when p != NULL (SIMT kernel).
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API size_t rmnet_memory_reader_workspace_bytes(int n, int T, int h, int w);
+RMNET_API int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const float *q_key,
+                                const float *q_val, int n, int T, int h, int w, int elem_format,
+                                int precision, int impl, float *mem_val, float *p, void *workspace,
+                                size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * flow_affine_transformation.update_optical_flow(of, M1, M2)   (flow_affine_transformation.cpp:39-85)
+ *   of [H,W,2] f32, m1_host / m2_host: 6 floats each (row-major 2x3, read on the host at call time),
+ *   out [H,W,2] f32.  Bit-exact with the reference's -O2 (no-FMA) build.
+ *   The *_host variant takes HOST arrays (what the NumPy-facing module passes), stages them through
+ *   `dev_scratch` (>= 2*H*W*2*4 bytes of device memory) and synchronises before returning.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_update_optical_flow(const float *of, const float *m1_host, const float *m2_host, int H, int W,
+                              float *out, void *stream);
+RMNET_API int rmnet_update_optical_flow_host(const float *of_host, const float *m1_host, const float *m2_host,
+                                   int H, int W, float *out_host, void *dev_scratch,
+                                   size_t dev_scratch_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMNET_B200_H_ */

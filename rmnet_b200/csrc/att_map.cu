@@ -1,0 +1,429 @@
+// att_map.cu -- regional attention-map generator, flow warp, and the fused warp+bbox kernel.
+//
+// Replaces (see include/rmnet_b200.h for the ABI):
+//   extensions/reg_att_map_generator/reg_att_map_generator.cu:15-123   (1 block x 512 threads, 5 global
+//       atomics per foreground pixel)  ->  multi-CTA vectorised scan, REDUX warp reductions, one atomic
+//       set per CTA, last-CTA finalise, self-cleaning workspace.
+//   models/rmnet.py:252-278 RMNet.warp (~15 ATen kernels + 2 grid_samples + a CPU-built grid)
+//       ->  one elementwise kernel; and fused with the generator (get_att_map, :280-287) so the warped
+//       mask never touches HBM.
+// All kernels are HBM-bound scans: coalesced (128-bit where alignment allows) loads, grids sized to
+// several CTAs per SM on 148 SMs.
+#include "common.cuh"
+
+namespace rmnet {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWsIntsPerChannel = 8;  // cnt, inv_xmin, xmax, inv_ymin, ymax, ticket, -, -
+
+// ---- per-thread bbox accumulator -------------------------------------------------------------
+struct BoxAcc {
+  int cnt, xmin, xmax, ymin, ymax;
+  __device__ __forceinline__ void init() { cnt = 0; xmin = 32767; xmax = 0; ymin = 32767; ymax = 0; }
+  __device__ __forceinline__ void hit(int x, int y) {
+    ++cnt;
+    xmin = min(xmin, x); xmax = max(xmax, x);
+    ymin = min(ymin, y); ymax = max(ymax, y);
+  }
+  __device__ __forceinline__ void warp_reduce() {
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    xmin = __reduce_min_sync(0xffffffffu, xmin);
+    xmax = __reduce_max_sync(0xffffffffu, xmax);
+    ymin = __reduce_min_sync(0xffffffffu, ymin);
+    ymax = __reduce_max_sync(0xffffffffu, ymax);
+  }
+};
+
+// Accumulate a CTA-level result into the global (zero-identity) workspace of one channel.
+// mins are stored as max(32767 - v) so that an all-zero workspace is the identity for every field.
+__device__ __forceinline__ void ws_accumulate(int *ws, const BoxAcc &a) {
+  if (a.cnt > 0) {
+    atomicAdd(ws + 0, a.cnt);
+    atomicMax(ws + 1, 32767 - a.xmin);
+    atomicMax(ws + 2, a.xmax);
+    atomicMax(ws + 3, 32767 - a.ymin);
+    atomicMax(ws + 4, a.ymax);
+  }
+}
+
+// reg_att_map_generator.cu:55-77 -- loosen / clamp, or full frame when too few points.
+// Reads AND clears the workspace accumulators (self-cleaning).
+__device__ __forceinline__ void finalize_channel(int *ws, int *bbox, int H, int W, int n_pts_threshold,
+                                                 int loose) {
+  int cnt = atomicExch(ws + 0, 0);
+  int xmin = 32767 - atomicExch(ws + 1, 0);
+  int xmax = atomicExch(ws + 2, 0);
+  int ymin = 32767 - atomicExch(ws + 3, 0);
+  int ymax = atomicExch(ws + 4, 0);
+  int4 r;
+  if (cnt < n_pts_threshold) {
+    r = make_int4(0, W - 1, 0, H - 1);
+  } else {
+    r.x = xmin <= loose ? 0 : xmin - loose;
+    r.y = xmax + loose >= W ? W - 1 : xmax + loose;
+    r.z = ymin <= loose ? 0 : ymin - loose;
+    r.w = ymax + loose >= H ? H - 1 : ymax + loose;
+  }
+  *reinterpret_cast<int4 *>(bbox) = r;  // bboxes are [.,4] i32, 16 B aligned per entry
+}
+
+// ---- plain generator: grid (chunks, K-1, B) ----------------------------------------------------
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr, int n_pts_threshold, int loose,
+                 int elems_per_cta, int *__restrict__ bboxes, int *__restrict__ ws) {
+  const int b = blockIdx.z, i = blockIdx.y + 1;
+  const long long n_pixels = (long long)H * W;
+  const float *plane = mask + ((long long)b * K + i) * n_pixels;
+  int *ws_ch = ws + ((long long)b * (K + 1) + i) * kWsIntsPerChannel;
+  const long long begin = (long long)blockIdx.x * elems_per_cta;
+  const long long end = min(begin + (long long)elems_per_cta, n_pixels);
+
+  BoxAcc acc;
+  acc.init();
+  if (VEC == 4) {
+    // 128-bit loads, 4 independent requests in flight per thread
+    const float4 *p4 = reinterpret_cast<const float4 *>(plane);
+    for (long long j0 = begin + (long long)threadIdx.x * 4; j0 < end; j0 += (long long)kThreads * 4 * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        long long j = j0 + (long long)u * kThreads * 4;
+        v[u] = (j < end) ? __ldg(p4 + (j >> 2)) : make_float4(-1.f, -1.f, -1.f, -1.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        long long j = j0 + (long long)u * kThreads * 4;
+        if (j >= end) continue;
+        int y = (int)(j / W), x = (int)(j - (long long)y * W);
+        const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (e[k] >= thr) acc.hit(x, y);  // NaN compares false, as in the reference (:42)
+          if (++x == W) { x = 0; ++y; }
+        }
+      }
+    }
+  } else {
+    for (long long j = begin + threadIdx.x; j < end; j += kThreads) {
+      float v = __ldg(plane + j);
+      if (v >= thr) { int y = (int)(j / W); acc.hit((int)(j - (long long)y * W), y); }
+    }
+  }
+
+  __shared__ int s_red[kThreads / 32][5];
+  __shared__ bool s_last;
+  acc.warp_reduce();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { s_red[warp][0] = acc.cnt; s_red[warp][1] = acc.xmin; s_red[warp][2] = acc.xmax; s_red[warp][3] = acc.ymin; s_red[warp][4] = acc.ymax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    BoxAcc t;
+    t.init();
+    for (int wdx = 0; wdx < kThreads / 32; ++wdx) {
+      t.cnt += s_red[wdx][0];
+      t.xmin = min(t.xmin, s_red[wdx][1]); t.xmax = max(t.xmax, s_red[wdx][2]);
+      t.ymin = min(t.ymin, s_red[wdx][3]); t.ymax = max(t.ymax, s_red[wdx][4]);
+    }
+    ws_accumulate(ws_ch, t);
+    __threadfence();
+    int ticket = atomicAdd(ws_ch + 5, 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    finalize_channel(ws_ch, bboxes + ((long long)b * K + i) * 4, H, W, n_pts_threshold, loose);
+    atomicExch(ws_ch + 5, 0);
+    if (i == 1) *reinterpret_cast<int4 *>(bboxes + (long long)b * K * 4) = make_int4(0, 0, 0, 0);  // channel 0 (:104 zeros)
+  }
+}
+
+// ---- att_map fill from final bboxes: att[b,i,y,x] = 1 inside the box (reg_att_map_generator.cu:81-92) ----
+template <int VEC>
+__global__ void __launch_bounds__(kThreads)
+att_fill_kernel(const int *__restrict__ bboxes, int K, int H, int W, long long total, float *__restrict__ att) {
+  const long long n_pixels = (long long)H * W;
+  for (long long j = ((long long)blockIdx.x * kThreads + threadIdx.x) * VEC; j < total;
+       j += (long long)gridDim.x * kThreads * VEC) {
+    long long ch = j / n_pixels;  // = b*K + i
+    long long r = j - ch * n_pixels;
+    int y = (int)(r / W), x = (int)(r - (long long)y * W);
+    int i = (int)(ch % K);
+    const int4 bb = __ldg(reinterpret_cast<const int4 *>(bboxes) + ch);
+    float e[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      e[k] = (i != 0 && x >= bb.x && x <= bb.y && y >= bb.z && y <= bb.w) ? 1.0f : 0.0f;
+      if (++x == W) { x = 0; ++y; }
+    }
+    if (VEC == 4) *reinterpret_cast<float4 *>(att + j) = make_float4(e[0], e[1], e[2], e[3]);
+    else att[j] = e[0];
+  }
+}
+
+// ---- flow warp sample point (models/rmnet.py:263-273 on torch's CUDA backend) -------------------
+struct Tap {
+  int x0, y0;           // north-west corner (may be out of bounds)
+  float nw, ne, sw, se; // bilinear weights
+  float valid;          // validity mask in {0,1}  (:272-275)
+};
+__device__ __forceinline__ Tap make_tap(int x, int y, float fx, float fy, int H, int W, float inv_w, float inv_h) {
+  Tap t;
+  // vgrid = grid + flow (:263); 2.0*v / max(W-1,1) - 1.0 (:265-266): ATen's CUDA div-by-scalar multiplies by the
+  // host-computed reciprocal (BinaryDivTrueKernel.cu); each op is a separately rounded fp32 kernel.
+  float gx = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, __fadd_rn((float)x, fx)), inv_w), 1.0f);
+  float gy = __fsub_rn(__fmul_rn(__fmul_rn(2.0f, __fadd_rn((float)y, fy)), inv_h), 1.0f);
+  // grid_sampler_unnormalize(align_corners=True): ((coord + 1) / 2) * (size - 1)   (GridSampler.cuh:23-31)
+  float ix = __fmul_rn(__fmul_rn(__fadd_rn(gx, 1.0f), 0.5f), (float)(W - 1));
+  float iy = __fmul_rn(__fmul_rn(__fadd_rn(gy, 1.0f), 0.5f), (float)(H - 1));
+  float flx = floorf(ix), fly = floorf(iy);
+  // clamp before the float->int cast (only matters for non-finite / absurd flows; keeps taps out of bounds)
+  t.x0 = (flx > -2.0f && flx < (float)W + 1.0f) ? (int)flx : -2;
+  t.y0 = (fly > -2.0f && fly < (float)H + 1.0f) ? (int)fly : -2;
+  float wx1 = __fsub_rn(ix, flx), wy1 = __fsub_rn(iy, fly);
+  float wx0 = __fsub_rn(__fadd_rn(flx, 1.0f), ix), wy0 = __fsub_rn(__fadd_rn(fly, 1.0f), iy);
+  t.nw = __fmul_rn(wx0, wy0); t.ne = __fmul_rn(wx1, wy0);
+  t.sw = __fmul_rn(wx0, wy1); t.se = __fmul_rn(wx1, wy1);
+  const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  float ones = 0.0f;  // grid_sample of the ones tensor: acc = fma(1, w, acc) in nw, ne, sw, se order
+  if (xin0 && yin0) ones = __fmaf_rn(1.0f, t.nw, ones);
+  if (xin1 && yin0) ones = __fmaf_rn(1.0f, t.ne, ones);
+  if (xin0 && yin1) ones = __fmaf_rn(1.0f, t.sw, ones);
+  if (xin1 && yin1) ones = __fmaf_rn(1.0f, t.se, ones);
+  float m = ones;
+  if (m < 0.9999f) m = 0.0f;  // :274
+  if (m > 0.0f) m = 1.0f;     // :275
+  t.valid = m;
+  return t;
+}
+__device__ __forceinline__ float sample_tap(const float *__restrict__ plane, const Tap &t, int H, int W) {
+  const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  const float *r0 = plane + (long long)t.y0 * W + t.x0;
+  float acc = 0.0f;  // GridSampler.cu: out_acc += v * w under nvcc -fmad=true
+  if (xin0 && yin0) acc = __fmaf_rn(__ldg(r0), t.nw, acc);
+  if (xin1 && yin0) acc = __fmaf_rn(__ldg(r0 + 1), t.ne, acc);
+  if (xin0 && yin1) acc = __fmaf_rn(__ldg(r0 + W), t.sw, acc);
+  if (xin1 && yin1) acc = __fmaf_rn(__ldg(r0 + W + 1), t.se, acc);
+  return __fmul_rn(acc, t.valid);  // img1 * mask (:277)
+}
+
+// ---- literal RMNet.warp: one thread per pixel, loop over channels --------------------------------
+__global__ void __launch_bounds__(kThreads)
+warp_kernel(const float *__restrict__ img0, const float *__restrict__ flow, int C, int H, int W, float inv_w,
+            float inv_h, float *__restrict__ img1, float *__restrict__ valid) {
+  const int b = blockIdx.y;
+  const long long n_pixels = (long long)H * W;
+  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (j >= n_pixels) return;
+  const int y = (int)(j / W), x = (int)(j - (long long)y * W);
+  const float *fl = flow + (long long)b * 2 * n_pixels;
+  const Tap t = make_tap(x, y, __ldg(fl + j), __ldg(fl + n_pixels + j), H, W, inv_w, inv_h);
+  for (int c = 0; c < C; ++c) {
+    const long long off = ((long long)b * C + c) * n_pixels;
+    img1[off + j] = sample_tap(img0 + off, t, H, W);
+    if (valid) valid[off + j] = t.valid;
+  }
+}
+
+// ---- fused warp + threshold + bbox: grid (pixel tiles, B) ----------------------------------------
+constexpr int kPixPerThread = 4;
+__global__ void __launch_bounds__(kThreads)
+warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
+                 float inv_w, float inv_h, float thr, int n_pts_threshold, int loose, int *__restrict__ bboxes,
+                 int *__restrict__ ws) {
+  extern __shared__ int s_acc[];  // [K][5] CTA accumulators (zero identity, mins inverted)
+  __shared__ bool s_last;
+  const int b = blockIdx.y;
+  const long long n_pixels = (long long)H * W;
+  const float *fl = flow + (long long)b * 2 * n_pixels;
+  for (int k = threadIdx.x; k < K * 5; k += kThreads) s_acc[k] = 0;
+  __syncthreads();
+
+  Tap taps[kPixPerThread];
+  int px[kPixPerThread], py[kPixPerThread];
+  bool live[kPixPerThread];
+  const long long base = (long long)blockIdx.x * kThreads * kPixPerThread + threadIdx.x;
+#pragma unroll
+  for (int p = 0; p < kPixPerThread; ++p) {
+    const long long j = base + (long long)p * kThreads;
+    live[p] = j < n_pixels;
+    const long long jj = live[p] ? j : 0;
+    py[p] = (int)(jj / W);
+    px[p] = (int)(jj - (long long)py[p] * W);
+    taps[p] = make_tap(px[p], py[p], __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
+  }
+  const int lane = threadIdx.x & 31;
+  for (int i = 1; i < K; ++i) {
+    const float *plane = prev_mask + ((long long)b * K + i) * n_pixels;
+    BoxAcc acc;
+    acc.init();
+#pragma unroll
+    for (int p = 0; p < kPixPerThread; ++p) {
+      if (live[p] && sample_tap(plane, taps[p], H, W) >= thr) acc.hit(px[p], py[p]);
+    }
+    acc.warp_reduce();
+    if (lane == 0 && acc.cnt > 0) {
+      atomicAdd(&s_acc[i * 5 + 0], acc.cnt);
+      atomicMax(&s_acc[i * 5 + 1], 32767 - acc.xmin);
+      atomicMax(&s_acc[i * 5 + 2], acc.xmax);
+      atomicMax(&s_acc[i * 5 + 3], 32767 - acc.ymin);
+      atomicMax(&s_acc[i * 5 + 4], acc.ymax);
+    }
+  }
+  __syncthreads();
+  int *ws_b = ws + (long long)b * (K + 1) * kWsIntsPerChannel;
+  for (int i = 1 + threadIdx.x; i < K; i += kThreads) {
+    if (s_acc[i * 5] > 0) {
+      int *w = ws_b + i * kWsIntsPerChannel;
+      atomicAdd(w + 0, s_acc[i * 5 + 0]);
+      atomicMax(w + 1, s_acc[i * 5 + 1]);
+      atomicMax(w + 2, s_acc[i * 5 + 2]);
+      atomicMax(w + 3, s_acc[i * 5 + 3]);
+      atomicMax(w + 4, s_acc[i * 5 + 4]);
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int ticket = atomicAdd(ws_b + K * kWsIntsPerChannel, 1);
+    s_last = (ticket == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int i = threadIdx.x; i < K; i += kThreads) {
+      int *bb = bboxes + ((long long)b * K + i) * 4;
+      if (i == 0) *reinterpret_cast<int4 *>(bb) = make_int4(0, 0, 0, 0);
+      else finalize_channel(ws_b + i * kWsIntsPerChannel, bb, H, W, n_pts_threshold, loose);
+    }
+    if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);
+  }
+}
+
+// ---- closed-form /16 cell rectangles (models/rmnet.py:245, :307+:356) -----------------------------
+__global__ void cell_rects_kernel(const int *__restrict__ bboxes, int count, int pad_l, int pad_t, int h, int w,
+                                  int skip_every, int *__restrict__ rects) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  const int4 bb = reinterpret_cast<const int4 *>(bboxes)[idx];
+  int4 r;
+  // cell (cy,cx) is live iff the padded full-res att at (16cy,16cx) is 1  <=>  x0+pad_l <= 16cx <= x1+pad_l
+  r.x = max(0, (bb.x + pad_l + 15) >> 4);
+  r.y = min(w - 1, (bb.y + pad_l) >> 4);
+  r.z = max(0, (bb.z + pad_t + 15) >> 4);
+  r.w = min(h - 1, (bb.w + pad_t) >> 4);
+  if (skip_every > 0 && idx % skip_every == 0) r = make_int4(0, -1, 0, -1);  // channel 0: att_map is all zero
+  if (r.x > r.y || r.z > r.w) r = make_int4(0, -1, 0, -1);
+  reinterpret_cast<int4 *>(rects)[idx] = r;
+}
+
+int launch_fill(const int *bboxes, int B, int K, int H, int W, float *att_full, cudaStream_t st) {
+  const long long total = (long long)B * K * H * W;
+  const bool vec = ((long long)H * W) % 4 == 0 && W >= 4 && ((uintptr_t)att_full % 16 == 0);
+  const int per = vec ? 4 : 1;
+  long long blocks = (total / per + kThreads - 1) / kThreads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (vec) att_fill_kernel<4><<<(unsigned)blocks, kThreads, 0, st>>>(bboxes, K, H, W, total, att_full);
+  else att_fill_kernel<1><<<(unsigned)blocks, kThreads, 0, st>>>(bboxes, K, H, W, total, att_full);
+  RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
+int check_common(const void *mask, int B, int K, int H, int W, const int *bboxes, const void *ws, size_t ws_bytes) {
+  RMNET_CHECK_ARG(mask && bboxes && ws, "null pointer argument");
+  RMNET_CHECK_ARG(B > 0 && K > 1 && H > 0 && W > 0, "bad shape B=%d K=%d H=%d W=%d (need K >= 2)", B, K, H, W);
+  RMNET_CHECK_ARG(H <= 32767 && W <= 32767, "H, W must be <= 32767 (reference min-init, reg_att_map_generator.cu:32)");
+  RMNET_CHECK_ARG(B <= 65535, "B too large");
+  RMNET_CHECK_ARG((uintptr_t)bboxes % 16 == 0, "bboxes must be 16-byte aligned");
+  if (ws_bytes < rmnet_reg_att_map_workspace_bytes(B, K)) {
+    set_error("workspace too small: %zu < %zu", ws_bytes, rmnet_reg_att_map_workspace_bytes(B, K));
+    return RMNET_E_WORKSPACE;
+  }
+  return RMNET_OK;
+}
+
+}  // namespace
+}  // namespace rmnet
+
+using namespace rmnet;
+
+extern "C" {
+
+size_t rmnet_reg_att_map_workspace_bytes(int B, int K) {
+  return (size_t)B * (K + 1) * kWsIntsPerChannel * sizeof(int);
+}
+
+int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,
+                              int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes, float *att_full,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long n_pixels = (long long)H * W;
+  const bool vec = n_pixels % 4 == 0 && W >= 4 && ((uintptr_t)mask % 16 == 0);
+  // ~2 CTAs per SM per channel-batch: each CTA streams a contiguous chunk (multiple of the 4096-float tile)
+  long long want_ctas = 148LL * 4;
+  long long per_channel = (want_ctas + (long long)(K - 1) * B - 1) / ((long long)(K - 1) * B);
+  if (per_channel < 1) per_channel = 1;
+  long long elems = (n_pixels + per_channel - 1) / per_channel;
+  elems = (elems + 4095) / 4096 * 4096;
+  const int chunks = (int)((n_pixels + elems - 1) / elems);
+  dim3 grid(chunks, K - 1, B);
+  if (vec)
+    bbox_scan_kernel<4><<<grid, kThreads, 0, st>>>(mask, K, H, W, prob_threshold, n_pts_threshold,
+                                                   n_bbox_loose_pixels, (int)elems, bboxes, (int *)workspace);
+  else
+    bbox_scan_kernel<1><<<grid, kThreads, 0, st>>>(mask, K, H, W, prob_threshold, n_pts_threshold,
+                                                   n_bbox_loose_pixels, (int)elems, bboxes, (int *)workspace);
+  RMNET_LAUNCH_CHECK();
+  if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
+  return RMNET_OK;
+}
+
+int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, float *img1, float *valid,
+                       void *stream) {
+  RMNET_CHECK_ARG(img0 && flow && img1, "null pointer argument");
+  RMNET_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
+  const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
+  const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
+  dim3 grid((unsigned)(((long long)H * W + kThreads - 1) / kThreads), B);
+  warp_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img0, flow, C, H, W, inv_w, inv_h, img1, valid);
+  RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
+int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
+                               float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes,
+                               float *att_full, void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_common(prev_mask, B, K, H, W, bboxes, workspace, workspace_bytes);
+  if (rc) return rc;
+  RMNET_CHECK_ARG(flow != nullptr, "null flow");
+  RMNET_CHECK_ARG(K <= 1024, "K too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);
+  const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
+  const int per_cta = kThreads * kPixPerThread;
+  dim3 grid((unsigned)(((long long)H * W + per_cta - 1) / per_cta), B);
+  warp_bbox_kernel<<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h,
+                                                                prob_threshold, n_pts_threshold,
+                                                                n_bbox_loose_pixels, bboxes, (int *)workspace);
+  RMNET_LAUNCH_CHECK();
+  if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
+  return RMNET_OK;
+}
+
+int rmnet_cell_rects_from_bboxes(const int *bboxes, int count, int pad_l, int pad_t, int h, int w,
+                                 int skip_channel0_every, int *rects, void *stream) {
+  RMNET_CHECK_ARG(bboxes && rects && count > 0 && h > 0 && w > 0, "bad argument");
+  RMNET_CHECK_ARG((uintptr_t)bboxes % 16 == 0 && (uintptr_t)rects % 16 == 0, "bboxes/rects must be 16-byte aligned");
+  cell_rects_kernel<<<cdiv(count, 128), 128, 0, (cudaStream_t)stream>>>(bboxes, count, pad_l, pad_t, h, w,
+                                                                         skip_channel0_every, rects);
+  RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
+}  // extern "C"

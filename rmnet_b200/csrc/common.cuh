@@ -1,0 +1,150 @@
+// common.cuh -- shared host/device helpers of librmnet_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rmnet_b200.h"
+
+namespace rmnet {
+
+// thread-local error string + launch counter (the only mutable state of the library)
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define RMNET_CHECK_ARG(cond, ...)                 \
+  do {                                             \
+    if (!(cond)) {                                 \
+      ::rmnet::set_error(__VA_ARGS__);             \
+      return RMNET_E_INVALID;                      \
+    }                                              \
+  } while (0)
+
+#define RMNET_CUDA(call)                                                                      \
+  do {                                                                                        \
+    cudaError_t _e = (call);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::rmnet::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,                 \
+                         cudaGetErrorString(_e));                                             \
+      return RMNET_E_CUDA;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+#define RMNET_LAUNCH_CHECK()                       \
+  do {                                             \
+    ::rmnet::count_launch();                       \
+    RMNET_CUDA(cudaGetLastError());                \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---- memory-bank blob layout (see bank.cu) -------------------------------------------------
+// [meta: n_slots x 8 i32][vsum: 2 x n_slots x 512 f32][K hi][K lo][V hi][V lo]; sections 1024 B aligned.
+struct BankLayout {
+  int n_slots, cap;
+  size_t off_meta, off_vsum, off_khi, off_klo, off_vhi, off_vlo, total;
+};
+static inline BankLayout bank_layout(int n_slots, int cap) {
+  BankLayout L;
+  L.n_slots = n_slots;
+  L.cap = cap;
+  size_t o = 0;
+  L.off_meta = o; o = align_up(o + (size_t)n_slots * 8 * sizeof(int), 1024);
+  L.off_vsum = o; o = align_up(o + (size_t)n_slots * 2 * RMNET_CV * sizeof(float), 1024);
+  size_t kplane = (size_t)n_slots * cap * RMNET_CK * 2;
+  size_t vplane = (size_t)n_slots * cap * RMNET_CV * 2;
+  L.off_khi = o; o = align_up(o + kplane, 1024);
+  L.off_klo = o; o = align_up(o + kplane, 1024);
+  L.off_vhi = o; o = align_up(o + vplane, 1024);
+  L.off_vlo = o; o = align_up(o + vplane, 1024);
+  L.total = o;
+  return L;
+}
+// meta ints per slot
+enum { META_CELLS_C = 0, META_CELLS_T = 1, META_ZEROS_C = 2, META_ZEROS_T = 3, META_FRAMES_C = 4, META_FRAMES_T = 5, META_OVERFLOW = 6 };
+
+// Device view of a bank, passed by value to kernels.
+struct BankView {
+  int *meta;            // [n_slots][8]
+  float *vsum;          // [2][n_slots][512]  (0 = committed frames, 1 = temporary frame): sum of stored V per channel
+  uint16_t *khi, *klo;  // [n_slots][cap][128]
+  uint16_t *vhi, *vlo;  // [n_slots][512][cap]
+  int n_slots, cap;
+};
+static inline BankView bank_view(void *bank, int n_slots, int cap) {
+  BankLayout L = bank_layout(n_slots, cap);
+  char *b = (char *)bank;
+  BankView v;
+  v.meta = (int *)(b + L.off_meta);
+  v.vsum = (float *)(b + L.off_vsum);
+  v.khi = (uint16_t *)(b + L.off_khi);
+  v.klo = (uint16_t *)(b + L.off_klo);
+  v.vhi = (uint16_t *)(b + L.off_vhi);
+  v.vlo = (uint16_t *)(b + L.off_vlo);
+  v.n_slots = n_slots;
+  v.cap = cap;
+  return v;
+}
+
+// ---- split-KV partial-result workspace (see memory_read_*.cu, merge.cu) ---------------------
+// opart [n_splits][n_obj][512][nq_pad] f32 (unnormalised numerators), ml [n_splits][n_obj][2 halves][nq_pad][2] f32
+struct ReadWorkspace {
+  float *opart, *ml;
+  int n_splits, nq_pad;
+  size_t total;
+};
+enum { READ_MAX_SPLITS = 8 };
+static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N) {
+  ReadWorkspace W;
+  W.nq_pad = cdiv(N, 128) * 128;
+  W.n_splits = READ_MAX_SPLITS;
+  size_t o = 0;
+  W.opart = (float *)((char *)ws + o);
+  o = align_up(o + (size_t)W.n_splits * n_obj * RMNET_CV * W.nq_pad * sizeof(float), 1024);
+  W.ml = (float *)((char *)ws + o);
+  o = align_up(o + (size_t)W.n_splits * n_obj * 2 * W.nq_pad * 2 * sizeof(float), 1024);
+  W.total = o;
+  return W;
+}
+
+#ifdef __CUDACC__
+// 16-bit hi/lo split of an fp32 value.  fmt 0 = bf16, 1 = fp16.  x ~= hi + lo with |err| <= 2^-17|x| (bf16).
+__device__ __forceinline__ void split16(float x, int fmt, uint16_t &hi, uint16_t &lo) {
+  if (fmt == 0) {
+    __nv_bfloat16 h = __float2bfloat16_rn(x);
+    float r = x - __bfloat162float(h);
+    __nv_bfloat16 l = __float2bfloat16_rn(r);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(l);
+  } else {
+    __half h = __float2half_rn(x);
+    float r = x - __half2float(h);
+    __half l = __float2half_rn(r);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+  }
+}
+__device__ __forceinline__ float join16(uint16_t hi, uint16_t lo, int fmt) {
+  if (fmt == 0) return __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo));
+  return __half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo));
+}
+__device__ __forceinline__ float cvt16(uint16_t v, int fmt) {
+  return fmt == 0 ? __bfloat162float(__ushort_as_bfloat16(v)) : __half2float(__ushort_as_half(v));
+}
+// compact index -> cell position inside an inclusive cell rectangle (cx0,cx1,cy0,cy1) on an h x w grid
+__device__ __forceinline__ int rect_cells(const int4 r) {
+  int rw = r.y - r.x + 1, rh = r.w - r.z + 1;
+  return (rw > 0 && rh > 0) ? rw * rh : 0;
+}
+__device__ __forceinline__ int rect_pos(const int4 r, int i, int w) {
+  int rw = r.y - r.x + 1;
+  int cy = r.z + i / rw, cx = r.x + i % rw;
+  return cy * w + cx;
+}
+#endif
+
+}  // namespace rmnet

@@ -1,0 +1,120 @@
+// memory_read.cu -- host-side dispatch of the regional memory read (C ABI entry points).
+#include "common.cuh"
+
+namespace rmnet {
+int launch_memory_read_simt(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
+                            int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
+                            cudaStream_t st);
+int launch_memory_read_umma(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
+                            int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
+                            cudaStream_t st);
+int launch_merge(const BankView &bank, const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h,
+                 int w, int n_splits, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
+bool umma_supported(int cap_cells);
+
+namespace {
+__global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) reinterpret_cast<int4 *>(rects)[i] = make_int4(0, w - 1, 0, h - 1);
+}
+
+int pick_splits(int n_obj, int N, int q_tile) {
+  // enough CTAs for ~2 per SM on 148 SMs; the KV axis is split flash-decoding style, merged by merge.cu
+  const int base = cdiv(N, q_tile) * n_obj * 2;
+  int s = cdiv(296, base);
+  if (s < 1) s = 1;
+  if (s > READ_MAX_SPLITS) s = READ_MAX_SPLITS;
+  return s;
+}
+}  // namespace
+}  // namespace rmnet
+
+using namespace rmnet;
+extern "C" {
+
+int rmnet_has_umma(void) { return umma_supported(64) ? 1 : 0; }
+
+size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells) {
+  (void)cap_cells;
+  if (n_obj <= 0 || h <= 0 || w <= 0) return 0;
+  return read_workspace(nullptr, n_obj, h * w).total;
+}
+
+int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
+                           const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h, int w,
+                           int elem_format, int precision, int impl, float *mem_val, void *workspace,
+                           size_t workspace_bytes, void *stream) {
+  RMNET_CHECK_ARG(bank && q_key && q_val && mem_val && workspace, "null pointer argument");
+  RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
+  RMNET_CHECK_ARG(n_obj <= 65535, "too many objects");
+  RMNET_CHECK_ARG(elem_format == 0 || elem_format == 1, "elem_format must be 0 (bf16) or 1 (fp16)");
+  RMNET_CHECK_ARG(precision == RMNET_PREC_SPLIT3 || precision == RMNET_PREC_SINGLE, "bad precision mode");
+  RMNET_CHECK_ARG(q_rects == nullptr || (uintptr_t)q_rects % 16 == 0, "q_rects must be 16-byte aligned");
+  BankLayout L = bank_layout(n_slots, cap_cells);
+  if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
+  ReadWorkspace W = read_workspace(workspace, n_obj, h * w);
+  if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
+  if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
+  int rc, n_splits;
+  if (impl == RMNET_IMPL_UMMA) {
+    n_splits = pick_splits(n_obj, h * w, 128);
+    rc = launch_memory_read_umma(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
+  } else if (impl == RMNET_IMPL_SIMT) {
+    n_splits = pick_splits(n_obj, h * w, 64);
+    rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
+  } else {
+    set_error("unknown impl %d", impl);
+    return RMNET_E_INVALID;
+  }
+  if (rc) return rc;
+  return launch_merge(bv, q_val, q_obj_stride ? (q_obj_stride / RMNET_CK) * RMNET_CV : 0, q_rects, n_obj, h, w, n_splits,
+                      W, mem_val, st);
+}
+
+static size_t reader_scratch_layout(int n, int T, int h, int w, size_t *off_rects, size_t *off_read, int *cap) {
+  const int N = h * w;
+  *cap = cdiv(T * N, 64) * 64;
+  size_t o = align_up(bank_layout(n, *cap).total, 1024);
+  *off_rects = o; o = align_up(o + (size_t)n * 16, 1024);
+  *off_read = o; o += read_workspace(nullptr, n, N).total;
+  return o;
+}
+
+size_t rmnet_memory_reader_workspace_bytes(int n, int T, int h, int w) {
+  if (n <= 0 || T <= 0 || h <= 0 || w <= 0) return 0;
+  size_t a, b; int cap;
+  return reader_scratch_layout(n, T, h, w, &a, &b, &cap);
+}
+
+int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const float *q_key, const float *q_val, int n,
+                                int T, int h, int w, int elem_format, int precision, int impl, float *mem_val, float *p,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+  RMNET_CHECK_ARG(m_key && m_val && q_key && q_val && mem_val && workspace, "null pointer argument");
+  RMNET_CHECK_ARG(n > 0 && T > 0 && h > 0 && w > 0, "bad shape");
+  RMNET_CHECK_ARG((uintptr_t)workspace % 1024 == 0, "workspace must be 1024-byte aligned");
+  if (p != nullptr) { set_error("materialising p [n,T*h*w,h*w] is not implemented yet; pass p = NULL"); return RMNET_E_UNSUPPORTED; }
+  size_t off_rects, off_read; int cap;
+  const size_t need = reader_scratch_layout(n, T, h, w, &off_rects, &off_read, &cap);
+  if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu", workspace_bytes, need); return RMNET_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = h * w;
+  char *ws = (char *)workspace;
+  const size_t bank_bytes = bank_layout(n, cap).total;
+  int *rects = (int *)(ws + off_rects);
+  int rc = rmnet_bank_reset(ws, bank_bytes, n, cap, stream);
+  if (rc) return rc;
+  fill_dense_rects_kernel<<<cdiv(n, 128), 128, 0, st>>>(rects, n, h, w);
+  RMNET_LAUNCH_CHECK();
+  // pack every memory frame (dense rectangle: the literal signature carries no region information)
+  for (int t = 0; t < T; ++t) {
+    rc = rmnet_bank_memorize(ws, bank_bytes, n, cap, m_key + (size_t)t * N, (long long)RMNET_CK * T * N, (long long)T * N,
+                             m_val + (size_t)t * N, (long long)RMNET_CV * T * N, (long long)T * N, rects, n, h, w,
+                             elem_format, /*commit=*/1, stream);
+    if (rc) return rc;
+  }
+  return rmnet_bank_memory_read(ws, bank_bytes, n, cap, q_key, q_val, (long long)RMNET_CK * N, rects, n, h, w, elem_format,
+                                precision, impl, mem_val, ws + off_read, workspace_bytes - off_read, stream);
+}
+}

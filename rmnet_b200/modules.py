@@ -1,0 +1,114 @@
+"""Host-side mirror of the reference's operator interface for the hot path: same class names, forward()
+signatures, argument meaning and error behaviour as
+
+  extensions/reg_att_map_generator/__init__.py:14-33   RegionalAttentionMapGenerator(.Function)
+  models/rmnet.py:143-165                               MemoryReader
+  models/rmnet.py:252-287                               RMNet.warp / RMNet.get_att_map
+  models/rmnet.py:239-248, :355-361                     the regional parts of RMNet.memorize / RMNet.segment
+
+so they drop in under core/inference.py.  Compute is exclusively librmnet_b200.so.
+"""
+import torch
+
+from . import ops
+from ._lib import ELEM_BF16, RMNET_IMPL_AUTO, RMNET_PREC_SPLIT3
+
+
+class RegionalAttentionMapGeneratorFunction(torch.autograd.Function):
+    """extensions/reg_att_map_generator/__init__.py:14-24 (the backward returns ones, like the reference)."""
+
+    @staticmethod
+    def forward(ctx, mask, prob_threshold, n_pts_threshold, n_bbox_loose_pixels):
+        att_map, bbox = ops.reg_att_map_forward(mask, prob_threshold, n_pts_threshold, n_bbox_loose_pixels)
+        ctx.mark_non_differentiable(bbox)
+        return att_map, bbox
+
+    @staticmethod
+    def backward(ctx, grad_att_map, grad_bbox):
+        return torch.ones_like(grad_att_map), None, None, None
+
+
+class RegionalAttentionMapGenerator(torch.nn.Module):
+    """extensions/reg_att_map_generator/__init__.py:27-33."""
+
+    def forward(self, mask, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64):
+        return RegionalAttentionMapGeneratorFunction.apply(mask, prob_threshold, n_pts_threshold, n_bbox_loose_pixels)
+
+
+class MemoryReader(torch.nn.Module):
+    """models/rmnet.py:143-165.  forward(m_key, m_val, q_key, q_val) -> (mem_val, p).
+
+    `p` ([n, T*h*w, h*w], 210 MB per object at 480p / T=20) is never materialised by the fused kernel; the only
+    caller ignores it (`m4, viz = self.memory(...)`, models/rmnet.py:361), so None is returned in its place."""
+
+    def __init__(self, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16):
+        super().__init__()
+        self.precision, self.impl, self.elem_format = precision, impl, elem_format
+
+    def forward(self, m_key, m_val, q_key, q_val):
+        if any(t.requires_grad for t in (m_key, m_val, q_key, q_val)) and torch.is_grad_enabled():
+            raise RuntimeError("rmnet_b200.MemoryReader is inference-only (run under torch.no_grad())")
+        mem_val = ops.memory_reader_forward(m_key.contiguous(), m_val.contiguous(), q_key.contiguous(),
+                                            q_val.contiguous(), self.precision, self.impl, self.elem_format)
+        return mem_val, None
+
+
+def warp(img0, flow):
+    """RMNet.warp(self, img0, flow) -> (img1, mask), models/rmnet.py:252-278."""
+    return ops.warp(img0.contiguous(), flow.contiguous())
+
+
+def get_att_map(prev_mask, flow=None, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64):
+    """RMNet.get_att_map(self, prev_mask, flow=None) -> (att_map, bbox), models/rmnet.py:280-287."""
+    if flow is None:
+        att, bbox = ops.reg_att_map_forward(prev_mask.contiguous(), prob_threshold, n_pts_threshold, n_bbox_loose_pixels)
+    else:
+        att, bbox = ops.warp_att_map_forward(prev_mask.contiguous(), flow.contiguous(), prob_threshold, n_pts_threshold,
+                                             n_bbox_loose_pixels)
+    return att, bbox
+
+
+class RegionalMemory:
+    """The fused regional path of one clip (batch 1, as core/inference.py:26 runs it): owns the preallocated bank
+    and exposes the two per-frame steps with the tensors the reference has at hand at those points.
+
+      memorize(k4, v4, masks_padded, commit)  <->  models/rmnet.py:239-248 (+ the cat at :416-426)
+      read(k4q, v4q, prev_mask, flow, n_objects)  <->  :431 get_att_map + :307 pad + :355-361
+    """
+
+    def __init__(self, n_objects, frame_hw, max_frames, device, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
+                 elem_format=ELEM_BF16):
+        H, W = frame_hw
+        self.lw, self.uw, self.lh, self.uh = ops.pad_amounts(H, W)
+        self.Hp, self.Wp = H + self.lh + self.uh, W + self.lw + self.uw
+        self.h, self.w = self.Hp // 16, self.Wp // 16
+        self.n = int(n_objects)
+        self.precision, self.impl = precision, impl
+        self.bank = ops.MemoryBank(self.n, self.h, self.w, max_frames, device, elem_format)
+
+    def memorize(self, k4, v4, masks_padded, commit):
+        """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks_padded [1,K,Hp,Wp]: the
+        padded soft masks the reference feeds to get_att_map (:244).  Returns bboxes [1,K,4] (padded coordinates)."""
+        _, bboxes = ops.reg_att_map_forward(masks_padded, want_att=False)
+        rects = ops.cell_rects(bboxes, 0, 0, self.h, self.w, skip_channel0_every=bboxes.shape[1])
+        self.bank.memorize(k4, v4, rects[0, 1:self.n + 1].contiguous(), commit)
+        return bboxes
+
+    def read(self, k4q, v4q, prev_mask, flow):
+        """k4q [128,h,w], v4q [512,h,w]: kv_query outputs of the current frame (:315); prev_mask [1,K,H,W] and
+        flow [1,2,H,W] in UNPADDED coordinates (:431).  Returns (m4 [n,1024,h,w], curr_bbox [1,K,4])."""
+        _, bbox = ops.warp_att_map_forward(prev_mask, flow, want_att=False)
+        rects = ops.cell_rects(bbox, self.lw, self.lh, self.h, self.w, skip_channel0_every=bbox.shape[1])
+        m4 = self.bank.read(k4q, v4q, rects[0, 1:self.n + 1].contiguous(), self.n, self.precision, self.impl)
+        return m4, bbox
+
+
+def install(models_rmnet_module):
+    """Rebind the reference's names so that an unmodified core/inference.py builds an RMNet that runs on this
+    library (RMNet.__init__ looks the classes up at construction time, models/rmnet.py:187-189)."""
+    models_rmnet_module.MemoryReader = MemoryReader
+    models_rmnet_module.RegionalAttentionMapGenerator = RegionalAttentionMapGenerator
+    cls = models_rmnet_module.RMNet
+    cls.warp = lambda self, img0, flow: warp(img0, flow)
+    cls.get_att_map = lambda self, prev_mask, flow=None: get_att_map(prev_mask, flow)
+    return models_rmnet_module

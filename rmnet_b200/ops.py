@@ -1,0 +1,266 @@
+"""Torch-tensor-facing wrappers around the C ABI: device memory, streams and shape checks only.
+
+Every function takes CUDA float32 tensors, allocates outputs with torch's caching allocator, passes raw
+pointers + the current stream to librmnet_b200.so, and never synchronises.  Error behaviour mirrors the
+reference's CHECK_INPUT (reg_att_map_generator_cuda.cpp:14-19): non-CUDA / non-contiguous inputs raise RuntimeError.
+"""
+import math
+
+import torch
+
+from . import _lib
+from ._lib import (ELEM_BF16, ELEM_FP16, RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET_IMPL_UMMA, RMNET_PREC_SINGLE,
+                   RMNET_PREC_SPLIT3, check, lib)
+
+CK, CV = 128, 512
+_ws_cache = {}
+
+
+def umma_available():
+    return bool(lib().rmnet_has_umma())
+
+
+def _require(t, name, dtype=torch.float32):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}")
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _zero_ws(dev, nbytes):
+    """Self-cleaning generator workspace, one per (device, stream): zero-filled once."""
+    key = (dev.index, _stream(dev))
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 4096), dtype=torch.uint8, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def reg_att_map_forward(mask, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64, want_att=True):
+    """reg_att_map_generator.forward (reg_att_map_generator_cuda.cpp:26-38) -> [att_map, bboxes]."""
+    _require(mask, "mask")
+    B, K, H, W = mask.shape
+    dev = mask.device
+    with torch.cuda.device(dev):
+        bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
+        att = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if want_att else None
+        nws = lib().rmnet_reg_att_map_workspace_bytes(B, K)
+        ws = _zero_ws(dev, nws)
+        check(lib().rmnet_reg_att_map_forward(mask.data_ptr(), B, K, H, W, float(prob_threshold), int(n_pts_threshold),
+                                              int(n_bbox_loose_pixels), bboxes.data_ptr(),
+                                              att.data_ptr() if want_att else None, ws.data_ptr(), ws.numel(),
+                                              _stream(dev)), "reg_att_map_forward")
+    return [att, bboxes]
+
+
+def warp(img0, flow, want_mask=True):
+    """RMNet.warp (models/rmnet.py:252-278) -> (img1, mask)."""
+    _require(img0, "img0")
+    _require(flow, "flow")
+    B, C, H, W = img0.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise RuntimeError(f"flow must be [{B},2,{H},{W}]")
+    dev = img0.device
+    with torch.cuda.device(dev):
+        img1 = torch.empty_like(img0)
+        valid = torch.empty_like(img0) if want_mask else None
+        check(lib().rmnet_warp_forward(img0.data_ptr(), flow.data_ptr(), B, C, H, W, img1.data_ptr(),
+                                       valid.data_ptr() if want_mask else None, _stream(dev)), "warp_forward")
+    return img1, valid
+
+
+def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64,
+                         want_att=True):
+    """RMNet.get_att_map(prev_mask, flow) (models/rmnet.py:280-287), warp fused into the bbox scan."""
+    _require(prev_mask, "prev_mask")
+    _require(flow, "flow")
+    B, K, H, W = prev_mask.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise RuntimeError(f"flow must be [{B},2,{H},{W}]")
+    dev = prev_mask.device
+    with torch.cuda.device(dev):
+        bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
+        att = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if want_att else None
+        ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
+        check(lib().rmnet_warp_att_map_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W, float(prob_threshold),
+                                               int(n_pts_threshold), int(n_bbox_loose_pixels), bboxes.data_ptr(),
+                                               att.data_ptr() if want_att else None, ws.data_ptr(), ws.numel(),
+                                               _stream(dev)), "warp_att_map_forward")
+    return att, bboxes
+
+
+def cell_rects(bboxes, pad_l, pad_t, h, w, skip_channel0_every=0):
+    """Closed form of pad + F.interpolate(att_map, 1/16) for box-shaped att maps -> [..., 4] (cx0,cx1,cy0,cy1)."""
+    _require(bboxes, "bboxes", torch.int32)
+    dev = bboxes.device
+    count = bboxes.numel() // 4
+    with torch.cuda.device(dev):
+        rects = torch.empty_like(bboxes)
+        check(lib().rmnet_cell_rects_from_bboxes(bboxes.data_ptr(), count, int(pad_l), int(pad_t), h, w,
+                                                 int(skip_channel0_every), rects.data_ptr(), _stream(dev)), "cell_rects")
+    return rects
+
+
+def pad_amounts(h, w, d=16):
+    """utils/helpers.py:105-119 pad_divide_by -> (lw, uw, lh, uh)."""
+    new_h = h + d - h % d if h % d > 0 else h
+    new_w = w + d - w % d if w % d > 0 else w
+    lh, uh = (new_h - h) // 2, (new_h - h) - (new_h - h) // 2
+    lw, uw = (new_w - w) // 2, (new_w - w) - (new_w - w) // 2
+    return lw, uw, lh, uh
+
+
+class MemoryBank:
+    """Preallocated region-compacted memory bank of one clip (replaces the reference's `keys`/`values` tensors
+    and their per-frame torch.cat, models/rmnet.py:416-426).  Slot s holds object s+1."""
+
+    def __init__(self, n_slots, h, w, max_frames, device, elem_format=ELEM_BF16):
+        self.n_slots, self.h, self.w = int(n_slots), int(h), int(w)
+        self.max_frames = int(max_frames)
+        self.cap = ((self.max_frames * h * w + 63) // 64) * 64
+        self.device = torch.device(device)
+        self.elem_format = elem_format
+        self.nbytes = lib().rmnet_bank_bytes(self.n_slots, self.cap)
+        with torch.cuda.device(self.device):
+            self.blob = torch.empty(self.nbytes + 1024, dtype=torch.uint8, device=self.device)
+            off = (-self.blob.data_ptr()) % 1024
+            self.ptr = self.blob.data_ptr() + off
+            self._ws = torch.empty(lib().rmnet_memory_read_workspace_bytes(self.n_slots, h, w, self.cap) + 1024,
+                                   dtype=torch.uint8, device=self.device)
+            self._ws_ptr = self._ws.data_ptr() + ((-self._ws.data_ptr()) % 1024)
+        self.frames_committed = 0
+        self.has_temp = False
+        self.reset()
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            check(lib().rmnet_bank_reset(self.ptr, self.nbytes, self.n_slots, self.cap, _stream(self.device)), "bank_reset")
+        self.frames_committed = 0
+        self.has_temp = False
+
+    def memorize(self, k4, v4, rects, commit):
+        """k4 [n,128,h,w], v4 [n,512,h,w] (unmasked, per object), rects [n,4] int32 cell rectangles of this frame."""
+        _require(k4, "k4")
+        _require(v4, "v4")
+        _require(rects, "rects", torch.int32)
+        n = k4.shape[0]
+        N = self.h * self.w
+        if tuple(k4.shape) != (n, CK, self.h, self.w) or tuple(v4.shape) != (n, CV, self.h, self.w):
+            raise RuntimeError("k4 / v4 shape mismatch")
+        if rects.numel() != n * 4:
+            raise RuntimeError("rects must be [n,4]")
+        if self.frames_committed + 1 > self.max_frames:
+            raise RuntimeError(f"memory bank full: {self.frames_committed} committed frames, capacity {self.max_frames}")
+        with torch.cuda.device(self.device):
+            check(lib().rmnet_bank_memorize(self.ptr, self.nbytes, self.n_slots, self.cap, k4.data_ptr(), CK * N, N,
+                                            v4.data_ptr(), CV * N, N, rects.data_ptr(), n, self.h, self.w,
+                                            self.elem_format, 1 if commit else 0, _stream(self.device)), "bank_memorize")
+        if commit:
+            self.frames_committed += 1
+            self.has_temp = False
+        else:
+            self.has_temp = True
+
+    def read(self, q_key, q_val, q_rects, n_obj, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO):
+        """q_key [128,h,w] / q_val [512,h,w] (one frame shared by all objects) or [n,128,h,w] / [n,512,h,w];
+        q_rects [n,4] int32 or None (dense) -> mem_val [n,1024,h,w]."""
+        _require(q_key, "q_key")
+        _require(q_val, "q_val")
+        N = self.h * self.w
+        shared = q_key.dim() == 3
+        if q_rects is not None:
+            _require(q_rects, "q_rects", torch.int32)
+        with torch.cuda.device(self.device):
+            out = torch.empty((n_obj, 2 * CV, self.h, self.w), dtype=torch.float32, device=self.device)
+            check(lib().rmnet_bank_memory_read(self.ptr, self.nbytes, self.n_slots, self.cap, q_key.data_ptr(),
+                                               q_val.data_ptr(), 0 if shared else CK * N,
+                                               q_rects.data_ptr() if q_rects is not None else None, n_obj, self.h,
+                                               self.w, self.elem_format, precision, impl, out.data_ptr(), self._ws_ptr,
+                                               self._ws.numel() - 1024, _stream(self.device)), "bank_memory_read")
+        return out
+
+    def stats(self):
+        import numpy as np
+        out = np.zeros((self.n_slots, 8), np.int32)
+        with torch.cuda.device(self.device):
+            check(lib().rmnet_bank_stats_host(self.ptr, self.n_slots, self.cap, out.ctypes.data, _stream(self.device)),
+                  "bank_stats")
+        return out
+
+
+_reader_ws = {}
+
+
+def memory_reader_forward(m_key, m_val, q_key, q_val, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
+                          elem_format=ELEM_BF16):
+    """Literal MemoryReader.forward (models/rmnet.py:147-165) -> mem_val [n,1024,h,w] (dense, region-agnostic)."""
+    for t, nm in ((m_key, "m_key"), (m_val, "m_val"), (q_key, "q_key"), (q_val, "q_val")):
+        _require(t, nm)
+    n, ck, T, h, w = m_key.shape
+    if ck != CK or m_val.shape[1] != CV or tuple(q_key.shape) != (n, CK, h, w) or tuple(q_val.shape) != (n, CV, h, w):
+        raise RuntimeError("MemoryReader shapes must be m_key [n,128,T,h,w], m_val [n,512,T,h,w], q_key [n,128,h,w], q_val [n,512,h,w]")
+    dev = m_key.device
+    with torch.cuda.device(dev):
+        need = lib().rmnet_memory_reader_workspace_bytes(n, T, h, w) + 1024
+        key = (dev.index, _stream(dev))
+        ws = _reader_ws.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _reader_ws[key] = ws
+        ptr = ws.data_ptr() + ((-ws.data_ptr()) % 1024)
+        out = torch.empty((n, 2 * CV, h, w), dtype=torch.float32, device=dev)
+        check(lib().rmnet_memory_reader_forward(m_key.data_ptr(), m_val.data_ptr(), q_key.data_ptr(), q_val.data_ptr(),
+                                                n, T, h, w, elem_format, precision, impl, out.data_ptr(), None, ptr,
+                                                ws.numel() - 1024, _stream(dev)), "memory_reader_forward")
+    return out
+
+
+def update_optical_flow_cuda(of, m1, m2):
+    """Device-tensor variant of update_optical_flow: of [H,W,2] CUDA f32; m1, m2 anything convertible to 6 floats."""
+    import numpy as np
+    _require(of, "of")
+    H, W = of.shape[:2]
+    a1 = np.ascontiguousarray(np.asarray(m1, dtype=np.float32).reshape(6))
+    a2 = np.ascontiguousarray(np.asarray(m2, dtype=np.float32).reshape(6))
+    with torch.cuda.device(of.device):
+        out = torch.empty_like(of)
+        check(lib().rmnet_update_optical_flow(of.data_ptr(), a1.ctypes.data, a2.ctypes.data, H, W, out.data_ptr(),
+                                              _stream(of.device)), "update_optical_flow")
+    return out
+
+
+_flow_scratch = {}
+
+
+def update_optical_flow(of, m1, m2):
+    """flow_affine_transformation.update_optical_flow(of, M1, M2) (flow_affine_transformation.cpp:39-85):
+    NumPy in, NumPy out; the arithmetic runs on the GPU (host buffers are staged through a device scratch).
+    Unlike the reference (no validation, .cpp:45-55) dtype / shape / contiguity are checked and converted."""
+    import numpy as np
+    of = np.ascontiguousarray(of, dtype=np.float32)
+    if of.ndim != 3 or of.shape[2] != 2:
+        raise ValueError("optical flow must be [H,W,2]")
+    a1 = np.ascontiguousarray(np.asarray(m1, dtype=np.float32).reshape(-1)[:6])
+    a2 = np.ascontiguousarray(np.asarray(m2, dtype=np.float32).reshape(-1)[:6])
+    if a1.size != 6 or a2.size != 6:
+        raise ValueError("affine matrices must be 2x3")
+    if not torch.cuda.is_available():
+        raise RuntimeError("rmnet_b200.update_optical_flow needs a CUDA device (no CPU fallback)")
+    H, W = of.shape[:2]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    need = 2 * of.nbytes
+    sc = _flow_scratch.get(dev.index)
+    if sc is None or sc.numel() < need:
+        sc = torch.empty(need, dtype=torch.uint8, device=dev)
+        _flow_scratch[dev.index] = sc
+    out = np.empty_like(of)
+    check(lib().rmnet_update_optical_flow_host(of.ctypes.data, a1.ctypes.data, a2.ctypes.data, H, W, out.ctypes.data,
+                                               sc.data_ptr(), sc.numel(), _stream(dev)), "update_optical_flow_host")
+    return out

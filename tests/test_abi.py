@@ -1,0 +1,91 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/rmnet_b200.h declares
+(no compute calls without a GPU), argument validation returns error codes, host-side helpers agree with the oracle."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import rmnet_b200
+from rmnet_b200 import _lib, ops
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "rmnet_b200.h")).read()
+    return sorted(set(re.findall(r"RMNET_API[^;(]*?\b(rmnet_\w+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared_symbols()
+    assert len(names) >= 19
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"librmnet_b200.so does not export {n}"
+    # and the ctypes prototypes cover exactly the header
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_abi_version_and_sizes():
+    L = rmnet_b200.lib()
+    assert L.rmnet_abi_version() == 1
+    assert L.rmnet_reg_att_map_workspace_bytes(1, 11) == 12 * 8 * 4
+    b1, b2 = L.rmnet_bank_bytes(3, 8128), L.rmnet_bank_bytes(3, 2 * 8128)
+    assert b1 > 3 * 8128 * 640 * 4 and b2 > b1
+    assert L.rmnet_bank_bytes(0, 64) == 0
+    assert L.rmnet_memory_reader_workspace_bytes(3, 5, 30, 54) > L.rmnet_bank_bytes(3, 5 * 1620)
+    assert L.rmnet_memory_read_workspace_bytes(3, 30, 54, 8128) >= 8 * 3 * 512 * 1664 * 4
+
+
+def test_argument_validation_returns_error_codes_without_touching_the_gpu():
+    L = rmnet_b200.lib()
+    assert L.rmnet_reg_att_map_forward(None, 1, 11, 8, 8, 0.5, 10, 64, None, None, None, 0, None) == -1
+    assert b"null" in L.rmnet_last_error()
+    assert L.rmnet_warp_forward(None, None, 1, 1, 8, 8, None, None, None) == -1
+    assert L.rmnet_update_optical_flow(None, None, None, 4, 4, None, None) == -1
+    assert L.rmnet_bank_reset(None, 0, 1, 64, None) == -1
+    buf = ctypes.create_string_buffer(4096)
+    # K must be >= 2 (channel 0 is the background), bad shapes are rejected before any launch
+    addr = (ctypes.addressof(buf) + 15) // 16 * 16
+    assert L.rmnet_reg_att_map_forward(addr, 1, 1, 8, 8, 0.5, 10, 64, addr, None, addr, 4096, None) == -1
+    assert L.rmnet_reg_att_map_forward(addr, 1, 11, 8, 8, 0.5, 10, 64, addr, None, addr, 8, None) == -3  # workspace too small
+
+
+def test_wrappers_reject_cpu_tensors_like_the_reference_check_input():
+    import torch
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):   # reg_att_map_generator_cuda.cpp:14,29
+        ops.reg_att_map_forward(torch.zeros(1, 2, 8, 8))
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        rmnet_b200.MemoryReader()(torch.zeros(1, 128, 1, 2, 2), torch.zeros(1, 512, 1, 2, 2),
+                                  torch.zeros(1, 128, 2, 2), torch.zeros(1, 512, 2, 2))
+    with pytest.raises(ValueError):
+        rmnet_b200.update_optical_flow(np.zeros((4, 4), np.float32), np.eye(2, 3), np.eye(2, 3))
+
+
+def test_pad_amounts_match_oracle():
+    for h, w in [(480, 854), (240, 432), (720, 1280), (33, 47), (481, 865), (16, 16)]:
+        assert ops.pad_amounts(h, w) == oracle.pad_amounts(h, w)
+
+
+def test_cell_rect_closed_form_equals_pad_then_downsample():
+    """The closed form the CUDA path uses (rmnet_cell_rects_from_bboxes) == the reference's pad + interpolate(1/16)
+    on a rectangular att map (models/rmnet.py:245, :307, :356), checked on the host restatement of the formula."""
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        H, W = int(rng.integers(17, 200)), int(rng.integers(17, 200))
+        x0, y0 = int(rng.integers(0, W)), int(rng.integers(0, H))
+        x1, y1 = int(rng.integers(x0, W)), int(rng.integers(y0, H))
+        att = np.zeros((1, H, W), np.float32)
+        att[0, y0:y1 + 1, x0:x1 + 1] = 1
+        attp, (lw, uw, lh, uh) = oracle.pad_divide_by(att)
+        a16 = oracle.downsample16(attp)[0]
+        h, w = a16.shape
+        cx0, cx1 = max(0, (x0 + lw + 15) >> 4), min(w - 1, (x1 + lw) >> 4)
+        cy0, cy1 = max(0, (y0 + lh + 15) >> 4), min(h - 1, (y1 + lh) >> 4)
+        ref = np.zeros_like(a16)
+        if cx0 <= cx1 and cy0 <= cy1:
+            ref[cy0:cy1 + 1, cx0:cx1 + 1] = 1
+        np.testing.assert_array_equal(a16, ref)
