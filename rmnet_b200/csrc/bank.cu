@@ -94,7 +94,7 @@ __global__ void bank_commit_kernel(BankView bank, int n_obj) {
   const int o = blockIdx.x;
   if (o >= n_obj) return;
   float *vc = bank.vsum + (size_t)o * RMNET_CV, *vt = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
-  for (int c = threadIdx.x; c < RMNET_CV; c += blockDim.x) vc[c] += vt[c];
+  for (int c = threadIdx.x; c < RMNET_CV; c += blockDim.x) { vc[c] += vt[c]; vt[c] = 0.f; }
   if (threadIdx.x == 0) {
     int *m = bank.meta + o * 8;
     m[META_CELLS_C] += m[META_CELLS_T];

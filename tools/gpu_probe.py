@@ -91,7 +91,7 @@ for name, (n, T) in {"c2_n3_T5": (3, 5), "c3_n5_T20": (5, 20)}.items():
     # regional boxes: ~24 % of the cells
     reg = torch.tensor([[10, 10 + 26, 5, 5 + 14]] * n, dtype=torch.int32, device=DEV)
     for label, rect in (("dense", dense), ("regional_f0.25", reg)):
-        bank = ops.MemoryBank(n, h, w, T, DEV)
+        bank = ops.MemoryBank(n, h, w, T + 1, DEV)
         k_t = [ks[:, :, t].contiguous() for t in range(T)]
         v_t = [vs[:, :, t].contiguous() for t in range(T)]
         for t in range(T):
