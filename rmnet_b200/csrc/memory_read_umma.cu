@@ -1,10 +1,474 @@
-// placeholder until the tcgen05 kernel lands (keeps the library linkable)
+// memory_read_umma.cu -- the fused regional memory read on Blackwell tensor cores (sm_100a).
+//
+// One CTA = (128 in-region queries) x (one object) x (one half of the 512 value channels) x (one KV split).
+// It streams the object's region-compacted bank in tiles of 64 memory cells and keeps everything on chip:
+//
+//   warp 0 : TMA producer for key tiles   (cp.async.bulk.tensor, SWIZZLE_128B, 3-stage mbarrier ring)
+//   warp 2 : TMA producer for value tiles (2-stage ring)
+//   warp 1 : MMA issuer -- one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
+//              S[128 q x 64 m]   = Q . K^T      A = Q  from TMEM, B = K tile (smem, K-major)
+//              O[128 q x 256 cv] += P . V^T     A = P  from TMEM, B = V tile (smem, K-major)
+//            in strict mode every product is the 3-term hi/lo split  Ah.Bh + Ah.Bl + Al.Bh  
+//   warps 4-7 : softmax warpgroup, one thread per query row (TMEM lane): tcgen05.ld S -> scale -> lazy online
+//            max -> exp2 -> hi/lo split of P -> tcgen05.st P over the S columns; rescales O in TMEM only when
+//            the running max grows by more than 2^8; epilogue tcgen05.ld O -> coalesced partial stores.
+//
+// TMEM (512 columns x 128 lanes): O [0,256) | S/P buffer 0 [256,320) | S/P buffer 1 [320,384) | Q hi [384,448) | Q lo [448,512)
+// Masked (never stored) memory cells and out-of-region queries are handled analytically by merge.cu.
+//
+// Reference math: models/rmnet.py:147-165 (MemoryReader.forward) with the regional masks of :245-248 / :355-358.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace rmnet {
-bool umma_supported(int) { return false; }
-int launch_memory_read_umma(const BankView &, const float *, long long, const int *, int, int, int, int, int, int,
-                            const ReadWorkspace &, cudaStream_t) {
-  set_error("tcgen05 memory-read kernel not built");
-  return RMNET_E_UNSUPPORTED;
+namespace {
+
+constexpr int QT = 128;   // queries per CTA  (UMMA M)
+constexpr int MT = 64;    // memory cells per KV tile
+constexpr int CVH = 256;  // value channels per CTA (UMMA N of the P.V product)
+constexpr int KST = 3;    // key-tile ring depth
+constexpr int VST = 2;    // value-tile ring depth
+constexpr int kThreads = 256;
+constexpr float kTau = 8.0f;  // lazy-rescale threshold (log2 units): P stays <= 2^8
+
+constexpr uint32_t K_PLANE_BYTES = MT * RMNET_CK * 2;       // 16 KB: [64 cells][128 ch] as two 8 KB SW128 blocks
+constexpr uint32_t K_STAGE_BYTES = 2 * K_PLANE_BYTES;       // hi + lo
+constexpr uint32_t V_PLANE_BYTES = CVH * MT * 2;            // 32 KB: [256 ch][64 cells]
+constexpr uint32_t V_STAGE_BYTES = 2 * V_PLANE_BYTES;
+constexpr uint32_t SMEM_TILES = KST * K_STAGE_BYTES + VST * V_STAGE_BYTES;  // 224 KB
+constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+// TMEM column map
+constexpr uint32_t TM_O = 0, TM_S0 = 256, TM_Q_HI = 384, TM_Q_LO = 448;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address      bits [0,14)
+  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major) = 16 B
+  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset  bits [32,46): 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                              // layout type: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = f32, A/B = bf16 (fmt 0) or f16 (fmt 1), both K-major, M = 128.
+__device__ __forceinline__ uint32_t umma_idesc(int fmt, int n) {
+  const uint32_t ab = (fmt == 0) ? 1u : 0u;  // F16F32Format: F16 = 0, BF16 = 1
+  return (1u << 4) | (ab << 7) | (ab << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(QT >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD16(addr, r, o)                                                                                         \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+               : "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),     \
+                 "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]),   \
+                 "=r"(r[o + 12]), "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])                                   \
+               : "r"(addr))
+#define TMEM_ST16(addr, r, o)                                                                                         \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" \
+               ::"r"(addr), "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), \
+                 "r"(r[o + 6]), "r"(r[o + 7]), "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]),         \
+                 "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15])                                       \
+               : "memory")
+
+// pack two fp32 into one 32-bit word of 16-bit values (element 0 in the low half) + the residual planes
+__device__ __forceinline__ void split_pack2(float x0, float x1, int fmt, uint32_t &hi, uint32_t &lo) {
+  uint16_t h0, l0, h1, l1;
+  split16(x0, fmt, h0, l0);
+  split16(x1, fmt, h1, l1);
+  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
+  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+
+struct Barriers {
+  uint64_t k_full[KST], k_empty[KST], v_full[VST], v_empty[VST];
+  uint64_t s_full[2], p_full[2], pv_done[2], q_ready;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
+                        const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
+                        const int *__restrict__ bank_meta, const float *__restrict__ q_key, long long q_obj_stride,
+                        const int *__restrict__ q_rects, int h, int w, int fmt, int use_lo, int n_splits,
+                        float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj,
+                        float *__restrict__ dbg) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  Barriers *bars = reinterpret_cast<Barriers *>(smem_al + SMEM_TILES);
+  const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
+
+  const int N = h * w;
+  const int o = blockIdx.y;
+  const int half = blockIdx.z & 1, split = blockIdx.z >> 1;
+  const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+  const int nq = rect_cells(qrect);
+  const int q0 = blockIdx.x * QT;
+  if (q0 >= nq) return;  // uniform per CTA, before any barrier / TMEM allocation
+
+  const int *meta = bank_meta + o * 8;
+  const int count = meta[META_CELLS_C] + meta[META_CELLS_T];
+  const int n_tiles = (count + MT - 1) / MT;
+  const int per = (n_tiles + n_splits - 1) / n_splits;
+  const int tile_begin = split * per;
+  const int n_it = max(0, min(n_tiles, tile_begin + per) - tile_begin);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
+    for (int i = 0; i < KST; ++i) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
+    for (int i = 0; i < VST; ++i) { mbar_init(smem_u32(&bars->v_full[i]), 1); mbar_init(smem_u32(&bars->v_empty[i]), 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&bars->s_full[i]), 1);
+      mbar_init(smem_u32(&bars->p_full[i]), 128);
+      mbar_init(smem_u32(&bars->pv_done[i]), 1);
+    }
+    mbar_init(smem_u32(&bars->q_ready), 128);
+    fence_barrier_init();
+  }
+  if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM: the smem footprint guarantees it)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars->tmem_base;
+
+  if (warp == 0) {
+    // ================= key-tile TMA producer =================
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % KST;
+        mbar_wait(smem_u32(&bars->k_empty[s]), ((it / KST) & 1) ^ 1);
+        const uint32_t full = smem_u32(&bars->k_full[s]);
+        mbar_expect_tx(full, use_lo ? K_STAGE_BYTES : K_PLANE_BYTES);
+        const uint32_t dst = k_smem + s * K_STAGE_BYTES;
+        const int m0 = (tile_begin + it) * MT;
+        tma_load_3d(dst, &map_khi, full, 0, m0, o);
+        tma_load_3d(dst + K_PLANE_BYTES / 2, &map_khi, full, 64, m0, o);
+        if (use_lo) {
+          tma_load_3d(dst + K_PLANE_BYTES, &map_klo, full, 0, m0, o);
+          tma_load_3d(dst + K_PLANE_BYTES + K_PLANE_BYTES / 2, &map_klo, full, 64, m0, o);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================= value-tile TMA producer =================
+    if (lane == 0) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % VST;
+        mbar_wait(smem_u32(&bars->v_empty[s]), ((it / VST) & 1) ^ 1);
+        const uint32_t full = smem_u32(&bars->v_full[s]);
+        mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
+        const uint32_t dst = v_smem + s * V_STAGE_BYTES;
+        const int m0 = (tile_begin + it) * MT;
+        tma_load_3d(dst, &map_vhi, full, m0, half * CVH, o);
+        if (use_lo) tma_load_3d(dst + V_PLANE_BYTES, &map_vlo, full, m0, half * CVH, o);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    const uint32_t idesc_qk = umma_idesc(fmt, MT), idesc_pv = umma_idesc(fmt, CVH);
+    auto issue_qk = [&](int it) {
+      const int s = it % KST, b = it & 1;
+      mbar_wait(smem_u32(&bars->k_full[s]), (it / KST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t kb = k_smem + s * K_STAGE_BYTES;
+        const uint32_t d = tmem + TM_S0 + b * MT;
+#pragma unroll
+        for (int kk = 0; kk < RMNET_CK / 16; ++kk) {
+          // 16 channels = 32 B inside the 128 B swizzle row; channels 64..127 live in the second 8 KB block
+          const uint32_t off = (kk >> 2) * (K_PLANE_BYTES / 2) + (kk & 3) * 32;
+          const uint64_t bh = umma_desc_sw128(kb + off);
+          umma_ts(d, tmem + TM_Q_HI + kk * 8, bh, idesc_qk, kk > 0 ? 1u : 0u);
+          if (use_lo) {
+            const uint64_t bl = umma_desc_sw128(kb + K_PLANE_BYTES + off);
+            umma_ts(d, tmem + TM_Q_HI + kk * 8, bl, idesc_qk, 1u);
+            umma_ts(d, tmem + TM_Q_LO + kk * 8, bh, idesc_qk, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars->k_empty[s]));  // key stage free once these MMAs retire
+        umma_commit(smem_u32(&bars->s_full[b]));   // scores ready for the softmax warpgroup
+      }
+      __syncwarp();
+    };
+    mbar_wait(smem_u32(&bars->q_ready), 0);
+    tc_fence_after();
+    if (n_it > 0) issue_qk(0);
+    if (n_it > 1) issue_qk(1);
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it % VST, b = it & 1;
+      mbar_wait(smem_u32(&bars->p_full[b]), (it >> 1) & 1);
+      mbar_wait(smem_u32(&bars->v_full[s]), (it / VST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t vb = v_smem + s * V_STAGE_BYTES;
+        const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
+#pragma unroll
+        for (int kk = 0; kk < MT / 16; ++kk) {
+          const uint64_t bh = umma_desc_sw128(vb + kk * 32);
+          umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
+          if (use_lo) {
+            const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
+            umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
+            umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars->v_empty[s]));
+        umma_commit(smem_u32(&bars->pv_done[b]));
+      }
+      __syncwarp();
+      if (it + 2 < n_it) issue_qk(it + 2);  // overwrites the S/P buffer PV(it) just consumed: in-order on the tensor pipe
+    }
+  } else if (warp >= 4) {
+    // ================= softmax / correction / epilogue warpgroup: thread <-> query row <-> TMEM lane =================
+    const int row = threadIdx.x - 128;                  // 0..127
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t t_base = tmem + lane_base;
+    const int n = q0 + row;
+    const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
+
+    // ---- Q rows -> 16-bit hi/lo planes in TMEM (A operand of the score product), 32 channels per pass
+    {
+      const bool live = n < nq;
+      const float *qp = q_key + (long long)o * q_obj_stride + (live ? rect_pos(qrect, n, w) : 0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < RMNET_CK; c0 += 32) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x0 = live ? __ldg(qp + (long long)(c0 + 2 * j) * N) : 0.f;
+          const float x1 = live ? __ldg(qp + (long long)(c0 + 2 * j + 1) * N) : 0.f;
+          split_pack2(x0, x1, fmt, hi[j], lo[j]);
+        }
+        TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
+        TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->q_ready));
+    }
+
+    float m_ref = -INFINITY, l_sum = 0.f;
+    for (int it = 0; it < n_it; ++it) {
+      const int b = it & 1;
+      const uint32_t s_addr = t_base + TM_S0 + b * MT;
+      mbar_wait(smem_u32(&bars->s_full[b]), (it >> 1) & 1);
+      tc_fence_after();
+      uint32_t sr[MT];
+      TMEM_LD16(s_addr, sr, 0);
+      TMEM_LD16(s_addr + 16, sr, 16);
+      TMEM_LD16(s_addr + 32, sr, 32);
+      TMEM_LD16(s_addr + 48, sr, 48);
+      tc_wait_ld();
+      if (dbg && it == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+#pragma unroll
+        for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
+      }
+      const int valid = count - (tile_begin + it) * MT;  // columns >= valid are beyond the stored cells
+      float mx = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < MT; ++j) {
+        float t = __uint_as_float(sr[j]) * scale;
+        t = (j < valid) ? t : -INFINITY;
+        sr[j] = __float_as_uint(t);
+        mx = fmaxf(mx, t);
+      }
+      if (it == 0) {
+        m_ref = (mx == -INFINITY) ? 0.f : mx;
+      } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
+        // lazy rescale of the O accumulator (rare after the first tiles): PV(it-1) must have retired, PV(it) cannot
+        // start before this warp arrives on p_full below.
+        mbar_wait(smem_u32(&bars->pv_done[(it - 1) & 1]), ((it - 1) >> 1) & 1);
+        tc_fence_after();
+        const float m_new = fmaxf(m_ref, mx);
+        const float f = exp2f(m_ref - m_new);
+#pragma unroll 1
+        for (int c = 0; c < CVH; c += 32) {
+          uint32_t orr[32];
+          TMEM_LD16(t_base + TM_O + c, orr, 0);
+          TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * f);
+          TMEM_ST16(t_base + TM_O + c, orr, 0);
+          TMEM_ST16(t_base + TM_O + c + 16, orr, 16);
+        }
+        l_sum *= f;
+        m_ref = m_new;
+      }
+      // P = 2^(t - m_ref), split into 16-bit hi/lo planes, packed two cells per TMEM column over the S buffer
+      uint32_t ph[MT / 2], pl[MT / 2];
+#pragma unroll
+      for (int j = 0; j < MT / 2; ++j) {
+        const float p0 = exp2f(__uint_as_float(sr[2 * j]) - m_ref);
+        const float p1 = exp2f(__uint_as_float(sr[2 * j + 1]) - m_ref);
+        uint16_t h0, l0, h1, l1;
+        split16(p0, fmt, h0, l0);
+        split16(p1, fmt, h1, l1);
+        if (!use_lo) { l0 = 0; l1 = 0; }
+        // the denominator sums exactly what the tensor core will multiply (hi + lo), so num / den stays a convex combination
+        l_sum += (cvt16(h0, fmt) + cvt16(l0, fmt)) + (cvt16(h1, fmt) + cvt16(l1, fmt));
+        ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+        pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      }
+      TMEM_ST16(s_addr, ph, 0);
+      TMEM_ST16(s_addr + 16, ph, 16);
+      if (use_lo) {
+        TMEM_ST16(s_addr + 32, pl, 0);
+        TMEM_ST16(s_addr + 48, pl, 16);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->p_full[b]));
+    }
+
+    // ---- epilogue: unnormalised numerators + (max, sum) statistics for merge.cu
+    {
+      float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)split * n_obj + o) * 2 + half) * nq_pad + n;
+      *dst = make_float2(n_it > 0 ? m_ref : -INFINITY, l_sum);
+    }
+    if (n_it > 0) {
+      mbar_wait(smem_u32(&bars->pv_done[(n_it - 1) & 1]), ((n_it - 1) >> 1) & 1);
+      tc_fence_after();
+      float *ob = opart + (((size_t)split * n_obj + o) * RMNET_CV + half * CVH) * nq_pad + n;
+#pragma unroll 1
+      for (int c = 0; c < CVH; c += 32) {
+        uint32_t orr[32];
+        TMEM_LD16(t_base + TM_O + c, orr, 0);
+        TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ob[(size_t)(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
+      }
+      if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[QT * MT + row] = m_ref;
+    }
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---- host: TMA descriptors ------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;  // resolved once; benign race (idempotent)
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap *m, void *base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+             uint64_t stride2_bytes, uint32_t b0, uint32_t b1) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return RMNET_E_CUDA; }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RMNET_E_CUDA; }
+  return RMNET_OK;
+}
+
+thread_local float *g_dbg = nullptr;
+
+}  // namespace
+
+bool umma_supported(int cap_cells) { return cap_cells % 64 == 0; }
+
+int launch_memory_read_umma(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
+                            int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
+                            cudaStream_t st) {
+  RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
+  CUtensorMap mkh, mkl, mvh, mvl;
+  const uint64_t cap = bank.cap, ns = bank.n_slots;
+  int rc;
+  // keys  [slot][cell][128 ch] : box 64 ch x 64 cells (128 B rows)      values [slot][512 ch][cell] : box 64 cells x 256 ch
+  if ((rc = make_map(&mkh, bank.khi, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
+  if ((rc = make_map(&mkl, bank.klo, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
+  if ((rc = make_map(&mvh, bank.vhi, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
+  if ((rc = make_map(&mvl, bank.vlo, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
+  RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+  dim3 grid(cdiv(h * w, QT), n_obj, 2 * n_splits);
+  memory_read_umma_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, q_rects,
+                                                              h, w, fmt, precision == RMNET_PREC_SPLIT3 ? 1 : 0, n_splits,
+                                                              W.opart, W.ml, W.nq_pad, n_obj, g_dbg);
+  RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
 }  // namespace rmnet
+
+// development hook (not part of the public header): dump S of the first tile of CTA (0,0,0) into `ptr` (128*64 + 128 floats)
+extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_dump(float *ptr) { rmnet::g_dbg = ptr; }
