@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- the regional memory-read hot path of RMNet on B200, measured per frame.
+
+A "step" is ONE frame of one clip through the hot path, in the steady state of a clip:
+
+    memorise side :  generator(prev_mask padded [1,11,Hp,Wp]) -> cell rects -> pack k4/v4 of the previous frame
+                     into the memory bank as its temporary last frame          (models/rmnet.py:239-248, :416-426)
+    segment side  :  fused warp + threshold + bbox(prev_mask [1,11,H,W], flow) -> cell rects
+                     -> regional memory read for all objects -> mem_val [n,1024,h,w]   (:431, :307, :355-361, :147-165)
+
+The ResNet-50 encoders / decoder that produce k4/v4 and consume mem_val are the reference's cuDNN code and out of
+scope: their outputs are synthetic tensors of the right shape.  Metric: frames/sec of this path
+(BASELINE.json `metric`), `value` with inputs resident in HBM, `e2e` through the public API with pinned HOST buffers.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: single 480x864 clip, 3 objects, T=5 memory
+    "c2": dict(H=480, W=854, n=3, T=5, desc="480x854 (padded 480x864) clip frame, 3 objects, T=5 memory frames, K=11 mask channels"),
+    # BASELINE.json configs[2] / north_star target shape: 480p, 5 objects, T=20
+    "c3": dict(H=480, W=854, n=5, T=20, desc="480x854 (padded 480x864) clip frame, 5 objects, T=20 memory frames, K=11 mask channels"),
+}
+K_CH = 11
+METRIC = "480p VOS frames/sec (regional memory-read hot path)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# synthetic clip state: drifting rectangles, soft masks, N(0, 2 px) flow, N(0,1) key/value features
+# ------------------------------------------------------------------------------------------------------------
+def make_pool(wl, seed, pool):
+    import synth
+    H, W, n, T = wl["H"], wl["W"], wl["n"], wl["T"]
+    rng = np.random.default_rng(seed)
+    Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+    lw = (Wp - W) // 2
+    h, w = Hp // 16, Wp // 16
+    # object rectangles drifting a few pixels per frame
+    boxes = []
+    for _ in range(n):
+        bh, bw = int(rng.uniform(0.15, 0.45) * H), int(rng.uniform(0.15, 0.45) * W)
+        boxes.append([int(rng.integers(0, H - bh)), int(rng.integers(0, W - bw)), bh, bw, int(rng.integers(-3, 4)), int(rng.integers(-3, 4))])
+
+    def frame_mask(step):
+        lab = np.zeros((H, W), np.int64)
+        for o, (y0, x0, bh, bw, vy, vx) in enumerate(boxes, 1):
+            y = int(np.clip(y0 + vy * step, 0, H - bh))
+            x = int(np.clip(x0 + vx * step, 0, W - bw))
+            lab[y:y + bh, x:x + bw] = o
+        return synth.soft_masks(rng, lab, K_CH)
+
+    frames = []
+    for i in range(T + pool):
+        frames.append(dict(
+            mask=frame_mask(i),                                                       # [K,H,W] soft probabilities
+            flow=synth.flow_field(rng, H, W, 2.0),                                    # [2,H,W]
+            k4=(rng.standard_normal((n, 128, h, w)) * 0.5).astype(np.float32),        # kv_memory(prev frame)
+            v4=rng.standard_normal((n, 512, h, w)).astype(np.float32),
+            qk=(rng.standard_normal((128, h, w)) * 0.5).astype(np.float32),           # kv_query(current frame)
+            qv=rng.standard_normal((512, h, w)).astype(np.float32)))
+    return dict(frames=frames, Hp=Hp, Wp=Wp, lw=lw, h=h, w=w)
+
+
+def pad_mask(mask, lw, Wp):
+    out = np.zeros(mask.shape[:-1] + (Wp,), np.float32)
+    out[..., lw:lw + mask.shape[-1]] = mask
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the same step on the host cores (cpu_baseline and --impl reference)
+# ------------------------------------------------------------------------------------------------------------
+class CpuClip:
+    """Reference algorithm on the CPU (oracle/: C restatement of the generator / warp, numpy-BLAS MemoryReader),
+    composed exactly as models/rmnet.py:244-248, :431, :307, :355-361 compose it (mask, then the DENSE reader)."""
+
+    def __init__(self, wl, pool):
+        import oracle
+        self.o, self.wl, self.pool = oracle, wl, pool
+        n, T = wl["n"], wl["T"]
+        self.keys, self.vals = [], []   # committed memory frames: masked [n,128,h,w], [n,512,h,w]
+        for t in range(T - 1):
+            k, v = self._masked_memory(pool["frames"][t])
+            self.keys.append(k)
+            self.vals.append(v)
+
+    def _masked_memory(self, fr):
+        n = self.wl["n"]
+        mp = pad_mask(fr["mask"], self.pool["lw"], self.pool["Wp"])
+        att, _ = self.o.reg_att_map(mp[None])                                       # :244
+        a16 = self.o.downsample16(att[0, 1:n + 1])                                  # :245
+        return fr["k4"] * a16[:, None], fr["v4"] * a16[:, None]                     # :247-248
+
+    def step(self, i):
+        n, T = self.wl["n"], self.wl["T"]
+        fr = self.pool["frames"][T - 1 + i % (len(self.pool["frames"]) - T + 1)]
+        k_t, v_t = self._masked_memory(fr)                                          # memorise (temporary frame)
+        m_key = np.stack(self.keys + [k_t], 2)
+        m_val = np.stack(self.vals + [v_t], 2)
+        att, _ = self.o.get_att_map(fr["mask"][None], fr["flow"][None], arith="cuda")   # :431
+        attp, _ = self.o.pad_divide_by(att[0, 1:n + 1])                             # :307
+        a16 = self.o.downsample16(attp)                                             # :356
+        qk = np.broadcast_to(fr["qk"], (n,) + fr["qk"].shape) * a16[:, None]        # :357
+        qv = np.broadcast_to(fr["qv"], (n,) + fr["qv"].shape) * a16[:, None]        # :358
+        mem_val, _ = self.o.memory_read(m_key, m_val, qk.astype(np.float32), qv.astype(np.float32))   # :361
+        return mem_val
+
+
+def time_cpu(wl, pool, steps, warmup):
+    clip = CpuClip(wl, pool)
+    for i in range(warmup):
+        clip.step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        out = clip.step(i)
+    dt = time.perf_counter() - t0
+    return steps / dt, dt / steps * 1e3, out
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows[-3:]]
+        sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(rows)}
+
+
+def algorithmic_work(counts_m, counts_q, N):
+    """SURVEY 8d / BASELINE.md 4: per object  flops = 1280 * M_r * N_r,  bytes = 4*[640*(M_r+N_r) + 1024*N]."""
+    flops = sum(1280.0 * m * q for m, q in zip(counts_m, counts_q))
+    byts = sum(4.0 * (640.0 * (m + q) + 1024.0 * N) for m, q in zip(counts_m, counts_q))
+    return flops, byts
+
+
+def run_gpu(args, wl, rank, world, local_rank):
+    import torch
+    import rmnet_b200
+    from rmnet_b200 import ops
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops", 1590.0))          # burst figure: the kernel is timed alone
+    peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+
+    n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
+    POOL = 8
+    pool = make_pool(wl, 1234 + rank, POOL)
+    h, w, lw, Wp = pool["h"], pool["w"], pool["lw"], pool["Wp"]
+    N = h * w
+    frames = pool["frames"]
+    precision = rmnet_b200.RMNET_PREC_SINGLE if args.precision == "single" else rmnet_b200.RMNET_PREC_SPLIT3
+    rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=dev, precision=precision)
+
+    def to_dev(fr):
+        return {k: torch.from_numpy(v).to(dev) for k, v in fr.items()} | {"maskp": torch.from_numpy(pad_mask(fr["mask"], lw, Wp)).to(dev)}
+
+    # steady state: T-1 committed memory frames, the T-th is rewritten every step as the temporary frame
+    for t in range(T - 1):
+        d = to_dev(frames[t])
+        rm.memorize(d["k4"], d["v4"], d["maskp"][None].contiguous(), commit=True)
+    dframes = [to_dev(fr) for fr in frames[T - 1:]]
+    hframes = [{k: torch.from_numpy(v).pin_memory() for k, v in fr.items()} | {"maskp": torch.from_numpy(pad_mask(fr["mask"], lw, Wp)).pin_memory()}
+               for fr in frames[T - 1:]]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    out_host = torch.empty((n, 1024, h, w), dtype=torch.float32).pin_memory()
+
+    def step_dev(d):
+        rm.memorize(d["k4"], d["v4"], d["maskp"][None], commit=False)
+        m4, _ = rm.read(d["qk"], d["qv"], d["mask"][None], d["flow"][None])
+        return m4
+
+    def step_host(hf):
+        d = {k: v.to(dev, non_blocking=True) for k, v in hf.items() if k in ("mask", "maskp", "flow", "k4", "v4", "qk", "qv")}
+        m4 = step_dev(d)
+        out_host.copy_(m4, non_blocking=True)
+        return m4
+
+    h2d = sum(hframes[0][k].numel() * 4 for k in ("mask", "maskp", "flow", "k4", "v4", "qk", "qv"))
+    d2h = out_host.numel() * 4
+
+    if world > 1:
+        import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    for i in range(max(args.warmup, 3)):
+        step_dev(dframes[i % len(dframes)])
+        step_host(hframes[i % len(hframes)])
+    torch.cuda.synchronize()
+
+    # ---- timed: K steps, device time by CUDA events on the launching stream, L2 flushed between steps
+    L = rmnet_b200.lib()
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+    barrier()
+    t_begin = time.perf_counter()
+    L.rmnet_launch_count_reset()
+    evs = []
+    for i in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        m4 = step_dev(dframes[i % len(dframes)])
+        b.record()
+        evs.append((a, b))
+    barrier()
+    launches = int(L.rmnet_launch_count())
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    dev_ms = float(np.sum(step_ms))
+
+    # ---- e2e: same steps through the public API with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_host(hframes[i % len(hframes)])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t_end = time.perf_counter()
+    clk = clocks.stop(t_begin, t_end) if clocks else None
+
+    # ---- roofline of the dominant kernel (the split-KV attention kernel), timed alone with events
+    st = rm.bank.stats()
+    cells = (st[:n, 0] + st[:n, 1]).astype(np.int64)
+    _, bbq = ops.warp_att_map_forward(dframes[0]["mask"][None], dframes[0]["flow"][None], want_att=False)
+    rq = ops.cell_rects(bbq, lw, 0, h, w, skip_channel0_every=K_CH)[0, 1:n + 1].contiguous()
+    rq_h = rq.cpu().numpy()
+    nq = [max(0, int(r[1] - r[0] + 1)) * max(0, int(r[3] - r[2] + 1)) for r in rq_h]
+    flops, byts = algorithmic_work(cells.tolist(), nq, N)
+    passes = 1 if args.precision == "single" else 3
+    d0 = dframes[0]
+    kt, mt = [], []
+    for i in range(max(args.steps, 5)):
+        flush.zero_()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        rm.bank.read(d0["qk"], d0["qv"], rq, n, precision, stages=1, out=m4)
+        e1.record()
+        rm.bank.read(d0["qk"], d0["qv"], rq, n, precision, stages=2, out=m4)
+        e2.record()
+        torch.cuda.synchronize()
+        kt.append(e0.elapsed_time(e1))
+        mt.append(e1.elapsed_time(e2))
+    k_ms = float(np.mean(kt))
+    achieved_tf = flops * passes / (k_ms * 1e-3) / 1e12
+    roof = {"bound": "tensor", "kernel": "memory_read_umma_kernel", "achieved": achieved_tf, "peak": tc_peak, "unit": "TFLOP/s",
+            "frac": achieved_tf / tc_peak, "traffic": None, "peak_source": peak_src, "kernel_ms": k_ms, "merge_ms": float(np.mean(mt)),
+            "passes": passes, "algorithmic_gflop": flops / 1e9, "algorithmic_mbytes": byts / 1e6,
+            "hbm_achieved_gbs": byts / (k_ms * 1e-3) / 1e9, "hbm_frac": byts / (k_ms * 1e-3) / 1e9 / hbm_peak,
+            "in_region_fraction": float(np.mean([c / (T * N) for c in cells])), "share_of_step": k_ms / (dev_ms / args.steps)}
+    try:   # DRAM traffic per launch of the same kernel from the committed `ncu --set full` capture, when present
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        roof["traffic"] = tr.get(args.workload, {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+
+    # ---- max over ranks, trivial NCCL gather of a result checksum (north_star: "NCCL only for the result gather")
+    checksum = float(m4.double().sum().item())
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(t[0]), float(t[1])
+        sums = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+        dist.gather(torch.tensor([checksum], device=dev, dtype=torch.float64), sums, dst=0)
+    if rank != 0:
+        return None
+    fps = world * args.steps / (dev_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 hi/lo split x3, fp32 accumulate" if passes == 3 else "bf16 x1, fp32 accumulate", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path "
+                               "(generator + pack-at-memorise + fused warp/bbox + regional read of all objects)",
+                   "clips_per_gpu": 1, "parallelism": f"clip-parallel x{world} (no data-path collective)", "precision": args.precision,
+                   "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed", "pool_frames": POOL},
+        "e2e": {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches, "roofline": roof, "clocks": clk, "result_checksum": checksum,
+    }
+    return line, pool
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="split3", choices=["split3", "single"])
+    ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto, ~10-30 s)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        # The reference's own implementation of this path on the host cores.  MemoryReader / warp are Python (torch)
+        # and the tree does not travel to the GPU box, so this is the oracle port (numpy-BLAS + C), all host threads.
+        if rank != 0:
+            return
+        pool = make_pool(wl, 1234, 4)
+        steps = min(args.steps, 20 if args.workload == "c2" else 8)
+        fps, ms, _ = time_cpu(wl, pool, steps, min(args.warmup, 2))
+        cores = os.cpu_count()
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path", "device": "host CPU"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                             "sample": f"{steps} steps of the same workload (oracle/: C generator + warp, numpy-BLAS MemoryReader on {cores} threads)"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    res = run_gpu(args, wl, rank, world, local_rank)
+    if rank == 0:
+        line, pool = res
+        if world == 1:
+            steps = args.cpu_steps or (20 if args.workload == "c2" else 6)
+            fps, ms, _ = time_cpu(wl, make_pool(wl, 1234, 4), steps, 1)
+            cores = os.cpu_count()
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(), "ms_per_step": ms,
+                                    "sample": f"{steps} steps of the same workload on the host (oracle/: C generator + warp, numpy-BLAS MemoryReader, {cores} threads)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,10 +85,15 @@ RMNET_API int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, 
  *   img0 [B,C,H,W], flow [B,2,H,W] (ch 0 = x, ch 1 = y, pixels); img1 [B,C,H,W]; valid [B,C,H,W]
  *   (the reference's `mask` output: the same [H,W] validity plane broadcast over C), nullable.
  *   Bit-exact with the reference evaluated on torch's CUDA backend (reciprocal-multiply
- *   normalisation, FMA-chained bilinear taps, >= 0.9999 validity).
+ *   normalisation, FMA-chained bilinear taps, >= 0.9999 validity).  `sampler` selects the tap
+ *   accumulation order: RMNET_SAMPLER_CUDNN (ne,nw,sw,se: cudnnSpatialTfSamplerForward, what
+ *   F.grid_sample dispatches to by default on CUDA) or RMNET_SAMPLER_ATEN (nw,ne,sw,se: ATen's
+ *   own kernel, used when torch.backends.cudnn.enabled is False).
  * ------------------------------------------------------------------------------------------- */
-RMNET_API int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, float *img1,
-                       float *valid, void *stream);
+#define RMNET_SAMPLER_CUDNN 0
+#define RMNET_SAMPLER_ATEN 1
+RMNET_API int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, int sampler,
+                                 float *img1, float *valid, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * RMNet.get_att_map(prev_mask, flow) fused: warp + threshold + bbox in ONE pass, the warped mask
@@ -96,9 +101,9 @@ RMNET_API int rmnet_warp_forward(const float *img0, const float *flow, int B, in
  *   outputs / workspace as rmnet_reg_att_map_forward.
  * ------------------------------------------------------------------------------------------- */
 RMNET_API int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
-                               float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels,
-                               int *bboxes, float *att_full, void *workspace, size_t workspace_bytes,
-                               void *stream);
+                               int sampler, float prob_threshold, int n_pts_threshold,
+                               int n_bbox_loose_pixels, int *bboxes, float *att_full, void *workspace,
+                               size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Low-resolution cell rectangles: the closed form of
@@ -143,12 +148,17 @@ RMNET_API int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells
  *   q_rects [n_obj,4] cell rectangles of the query frame (device); NULL = dense (all cells).
  *   mem_val [n_obj,1024,h,w] f32: channels 0..511 the memory read, 512..1023 the (masked) q_val.
  *   workspace: rmnet_memory_read_workspace_bytes(...) bytes (partial results of the split-KV pass).
+ *   stages: RMNET_STAGE_ALL normally; RMNET_STAGE_PARTIAL / RMNET_STAGE_MERGE run only the split-KV
+ *     attention kernel / only the merge+scatter kernel (so a benchmark can time each launch alone).
  * ------------------------------------------------------------------------------------------- */
+#define RMNET_STAGE_PARTIAL 1
+#define RMNET_STAGE_MERGE 2
+#define RMNET_STAGE_ALL 3
 RMNET_API size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells);
 RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells,
                            const float *q_key, const float *q_val, long long q_obj_stride,
                            const int *q_rects, int n_obj, int h, int w, int elem_format,
-                           int precision, int impl, float *mem_val, void *workspace,
+                           int precision, int impl, int stages, float *mem_val, void *workspace,
                            size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------

@@ -60,7 +60,7 @@ def lib():
         L.oracle_pad_amounts.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p]
         L.oracle_pad2d.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _i32p, _f32p]
         L.oracle_downsample16_nearest.argtypes = [_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, _f32p]
-        L.oracle_warp.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+        L.oracle_warp.argtypes = [_f32p, _f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                   _f32p, _f32p]
         L.oracle_update_optical_flow.argtypes = [_f32p, _f32p, _f32p, ctypes.c_int, ctypes.c_int, _f32p]
         L.oracle_memory_read_f64.argtypes = [_f32p, _f32p, _f32p, _f32p, ctypes.c_int, ctypes.c_int,
@@ -114,14 +114,17 @@ def downsample16(att):
 
 def warp(img0, flow, arith="cuda"):
     """RMNet.warp, models/rmnet.py:252-278.  img0 [B,C,H,W], flow [B,2,H,W] -> (img1 [B,C,H,W], mask [B,C,H,W]).
-    ``arith`` = 'cpu' | 'cuda': which torch backend's floating-point evaluation order to mirror."""
+    ``arith`` selects which torch backend's floating-point evaluation order is mirrored:
+      'cpu'         true division, ATen tap order      (what the reference computes on a CPU-only box)
+      'cuda_native' reciprocal multiply, ATen tap order (CUDA with torch.backends.cudnn.enabled = False)
+      'cuda' / 'cuda_cudnn'  reciprocal multiply, cuDNN tap order (the reference's default GPU path)"""
     img0, flow = _c(img0), _c(flow)
     B, C, H, W = img0.shape
     img1 = np.empty_like(img0)
     valid = np.empty((B, 1, H, W), np.float32)
-    a = {"cpu": 0, "cuda": 1}[arith]
+    a, order = {"cpu": (0, 0), "cuda_native": (1, 0), "cuda": (1, 1), "cuda_cudnn": (1, 1)}[arith]
     for b in range(B):
-        lib().oracle_warp(img0[b], flow[b], C, H, W, a, img1[b], valid[b, 0])
+        lib().oracle_warp(img0[b], flow[b], C, H, W, a, order, img1[b], valid[b, 0])
     return img1, np.broadcast_to(valid, img0.shape).copy()
 
 

@@ -118,11 +118,16 @@ ORACLE_API void oracle_downsample16_nearest(const float *in, int C, int Hp, int 
  * (torch 2.11; both evaluate the same real-valued formula):
  *   0 = CPU path : true division  2*v / (W-1)            (ATen/native/cpu BinaryOpsKernel)
  *   1 = CUDA path: 2*v * (1/(W-1)) reciprocal multiply   (cuda/BinaryDivTrueKernel.cu, CPU-scalar divisor)
- * Both backends accumulate the four taps as an FMA chain in nw, ne, sw, se order,
- *   acc = fma(v_se, se, fma(v_sw, sw, fma(v_ne, ne, v_nw * nw)))
- * (cuda/GridSampler.cu under nvcc -fmad=true; cpu/GridSamplerKernel.cpp as built in the torch
- * 2.11 wheel -- established empirically: 0 mismatches vs F.grid_sample on CPU, while the
- * unfused sum mismatches ~7 % of pixels by 1 ulp).
+ * Every backend accumulates the four taps as an FMA chain; `tap_order` selects the order:
+ *   0 = nw, ne, sw, se : acc = fma(v_se, se, fma(v_sw, sw, fma(v_ne, ne, v_nw * nw)))
+ *       ATen's own kernels (cuda/GridSampler.cu under nvcc -fmad=true; cpu/GridSamplerKernel.cpp as built in
+ *       the torch 2.11 wheel) -- established empirically: 0 mismatches vs F.grid_sample on CPU and vs the CUDA
+ *       kernel with torch.backends.cudnn.enabled=False.
+ *   1 = ne, nw, sw, se : acc = fma(v_se, se, fma(v_sw, sw, fma(v_nw, nw, v_ne * ne)))
+ *       cudnnSpatialTfSamplerForward (cuDNN 9.x), which torch dispatches to on CUDA for bilinear / zeros /
+ *       align_corners=True when cuDNN is enabled (ATen/native/GridSampler.cpp cond_cudnn_grid_sampler) -- the
+ *       reference's default GPU path.  Established empirically on a B200: 0 mismatches in 12 288 samples, every
+ *       other of 200+ candidate orders / weight forms mismatches >= 11 % of the samples by 1 ulp.
  * Unnormalisation ((g+1)/2)*(size-1): ATen/native/cuda/GridSampler.cuh:23-31 (= GridSampler.h on CPU).
  * ---------------------------------------------------------------------------------- */
 static inline float oracle_norm_coord(float v, int size, int arith) {
@@ -133,7 +138,7 @@ static inline float oracle_norm_coord(float v, int size, int arith) {
   return t - 1.0f;
 }
 
-ORACLE_API int oracle_warp(const float *img0, const float *flow, int C, int H, int W, int arith,
+ORACLE_API int oracle_warp(const float *img0, const float *flow, int C, int H, int W, int arith, int tap_order,
                            float *img1, float *valid) {
   const long n_pixels = (long)H * W;
   for (int y = 0; y < H; ++y) {
@@ -160,8 +165,13 @@ ORACLE_API int oracle_warp(const float *img0, const float *flow, int C, int H, i
       int in_se = (x1 >= 0 && x1 < W && y1 >= 0 && y1 < H);
       /* sampled ones tensor (:272-273) */
       float ones = 0.0f;
-      if (in_nw) ones = fmaf(1.0f, nw, ones);
-      if (in_ne) ones = fmaf(1.0f, ne, ones);
+      if (tap_order == 0) {
+        if (in_nw) ones = fmaf(1.0f, nw, ones);
+        if (in_ne) ones = fmaf(1.0f, ne, ones);
+      } else {
+        if (in_ne) ones = fmaf(1.0f, ne, ones);
+        if (in_nw) ones = fmaf(1.0f, nw, ones);
+      }
       if (in_sw) ones = fmaf(1.0f, sw, ones);
       if (in_se) ones = fmaf(1.0f, se, ones);
       float m = ones;
@@ -175,8 +185,13 @@ ORACLE_API int oracle_warp(const float *img0, const float *flow, int C, int H, i
         float v_sw = in_sw ? p[(long)y1 * W + x0] : 0.0f;
         float v_se = in_se ? p[(long)y1 * W + x1] : 0.0f;
         float s = 0.0f;
-        if (in_nw) s = fmaf(v_nw, nw, s);
-        if (in_ne) s = fmaf(v_ne, ne, s);
+        if (tap_order == 0) {
+          if (in_nw) s = fmaf(v_nw, nw, s);
+          if (in_ne) s = fmaf(v_ne, ne, s);
+        } else {
+          if (in_ne) s = fmaf(v_ne, ne, s);
+          if (in_nw) s = fmaf(v_nw, nw, s);
+        }
         if (in_sw) s = fmaf(v_sw, sw, s);
         if (in_se) s = fmaf(v_se, se, s);
         img1[(long)c * n_pixels + j] = s * m; /* :277 */

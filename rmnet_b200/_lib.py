@@ -14,6 +14,7 @@ CSRC = os.path.join(_HERE, "csrc")
 RMNET_PREC_SPLIT3, RMNET_PREC_SINGLE = 0, 1
 RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET_IMPL_UMMA = 0, 1, 2
 ELEM_BF16, ELEM_FP16 = 0, 1
+SAMPLER_CUDNN, SAMPLER_ATEN = 0, 1
 
 _lock = threading.Lock()
 _lib = None
@@ -30,8 +31,8 @@ PROTOTYPES = {
     "rmnet_reg_att_map_workspace_bytes": (c_size_t, [c_int, c_int]),
     "rmnet_reg_att_map_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int, c_void_p,
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
-    "rmnet_warp_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "rmnet_warp_att_map_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+    "rmnet_warp_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "rmnet_warp_att_map_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_cell_rects_from_bboxes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rmnet_bank_bytes": (c_size_t, [c_int, c_int]),
@@ -41,7 +42,7 @@ PROTOTYPES = {
     "rmnet_bank_stats_host": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "rmnet_memory_read_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_bank_memory_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int,
-                                       c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_memory_reader_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_memory_reader_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -169,6 +169,7 @@ struct Tap {
   float nw, ne, sw, se; // bilinear weights
   float valid;          // validity mask in {0,1}  (:272-275)
 };
+template <int ORDER>  // 0 = cuDNN tap order (ne, nw, sw, se), 1 = ATen tap order (nw, ne, sw, se)
 __device__ __forceinline__ Tap make_tap(int x, int y, float fx, float fy, int H, int W, float inv_w, float inv_h) {
   Tap t;
   // vgrid = grid + flow (:263); 2.0*v / max(W-1,1) - 1.0 (:265-266): ATen's CUDA div-by-scalar multiplies by the
@@ -188,9 +189,14 @@ __device__ __forceinline__ Tap make_tap(int x, int y, float fx, float fy, int H,
   t.sw = __fmul_rn(wx0, wy1); t.se = __fmul_rn(wx1, wy1);
   const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
   const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  float ones = 0.0f;  // grid_sample of the ones tensor: acc = fma(1, w, acc) in nw, ne, sw, se order
-  if (xin0 && yin0) ones = __fmaf_rn(1.0f, t.nw, ones);
-  if (xin1 && yin0) ones = __fmaf_rn(1.0f, t.ne, ones);
+  float ones = 0.0f;  // grid_sample of the ones tensor: acc = fma(1, w, acc) in the sampler's tap order
+  if (ORDER == 1) {
+    if (xin0 && yin0) ones = __fmaf_rn(1.0f, t.nw, ones);
+    if (xin1 && yin0) ones = __fmaf_rn(1.0f, t.ne, ones);
+  } else {
+    if (xin1 && yin0) ones = __fmaf_rn(1.0f, t.ne, ones);
+    if (xin0 && yin0) ones = __fmaf_rn(1.0f, t.nw, ones);
+  }
   if (xin0 && yin1) ones = __fmaf_rn(1.0f, t.sw, ones);
   if (xin1 && yin1) ones = __fmaf_rn(1.0f, t.se, ones);
   float m = ones;
@@ -199,19 +205,26 @@ __device__ __forceinline__ Tap make_tap(int x, int y, float fx, float fy, int H,
   t.valid = m;
   return t;
 }
+template <int ORDER>
 __device__ __forceinline__ float sample_tap(const float *__restrict__ plane, const Tap &t, int H, int W) {
   const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
   const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
   const float *r0 = plane + (long long)t.y0 * W + t.x0;
-  float acc = 0.0f;  // GridSampler.cu: out_acc += v * w under nvcc -fmad=true
-  if (xin0 && yin0) acc = __fmaf_rn(__ldg(r0), t.nw, acc);
-  if (xin1 && yin0) acc = __fmaf_rn(__ldg(r0 + 1), t.ne, acc);
+  float acc = 0.0f;  // ATen GridSampler.cu: out_acc += v * w under nvcc -fmad=true; cuDNN: same chain, ne first
+  if (ORDER == 1) {
+    if (xin0 && yin0) acc = __fmaf_rn(__ldg(r0), t.nw, acc);
+    if (xin1 && yin0) acc = __fmaf_rn(__ldg(r0 + 1), t.ne, acc);
+  } else {
+    if (xin1 && yin0) acc = __fmaf_rn(__ldg(r0 + 1), t.ne, acc);
+    if (xin0 && yin0) acc = __fmaf_rn(__ldg(r0), t.nw, acc);
+  }
   if (xin0 && yin1) acc = __fmaf_rn(__ldg(r0 + W), t.sw, acc);
   if (xin1 && yin1) acc = __fmaf_rn(__ldg(r0 + W + 1), t.se, acc);
   return __fmul_rn(acc, t.valid);  // img1 * mask (:277)
 }
 
 // ---- literal RMNet.warp: one thread per pixel, loop over channels --------------------------------
+template <int ORDER>
 __global__ void __launch_bounds__(kThreads)
 warp_kernel(const float *__restrict__ img0, const float *__restrict__ flow, int C, int H, int W, float inv_w,
             float inv_h, float *__restrict__ img1, float *__restrict__ valid) {
@@ -221,16 +234,17 @@ warp_kernel(const float *__restrict__ img0, const float *__restrict__ flow, int 
   if (j >= n_pixels) return;
   const int y = (int)(j / W), x = (int)(j - (long long)y * W);
   const float *fl = flow + (long long)b * 2 * n_pixels;
-  const Tap t = make_tap(x, y, __ldg(fl + j), __ldg(fl + n_pixels + j), H, W, inv_w, inv_h);
+  const Tap t = make_tap<ORDER>(x, y, __ldg(fl + j), __ldg(fl + n_pixels + j), H, W, inv_w, inv_h);
   for (int c = 0; c < C; ++c) {
     const long long off = ((long long)b * C + c) * n_pixels;
-    img1[off + j] = sample_tap(img0 + off, t, H, W);
+    img1[off + j] = sample_tap<ORDER>(img0 + off, t, H, W);
     if (valid) valid[off + j] = t.valid;
   }
 }
 
 // ---- fused warp + threshold + bbox: grid (pixel tiles, B) ----------------------------------------
 constexpr int kPixPerThread = 4;
+template <int ORDER>
 __global__ void __launch_bounds__(kThreads)
 warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
                  float inv_w, float inv_h, float thr, int n_pts_threshold, int loose, int *__restrict__ bboxes,
@@ -254,7 +268,7 @@ warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ 
     const long long jj = live[p] ? j : 0;
     py[p] = (int)(jj / W);
     px[p] = (int)(jj - (long long)py[p] * W);
-    taps[p] = make_tap(px[p], py[p], __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
+    taps[p] = make_tap<ORDER>(px[p], py[p], __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
   }
   const int lane = threadIdx.x & 31;
   for (int i = 1; i < K; ++i) {
@@ -263,7 +277,7 @@ warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ 
     acc.init();
 #pragma unroll
     for (int p = 0; p < kPixPerThread; ++p) {
-      if (live[p] && sample_tap(plane, taps[p], H, W) >= thr) acc.hit(px[p], py[p]);
+      if (live[p] && sample_tap<ORDER>(plane, taps[p], H, W) >= thr) acc.hit(px[p], py[p]);
     }
     acc.warp_reduce();
     if (lane == 0 && acc.cnt > 0) {
@@ -384,33 +398,43 @@ int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, flo
   return RMNET_OK;
 }
 
-int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, float *img1, float *valid,
-                       void *stream) {
+int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, int sampler, float *img1,
+                       float *valid, void *stream) {
   RMNET_CHECK_ARG(img0 && flow && img1, "null pointer argument");
   RMNET_CHECK_ARG(B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535, "bad shape");
+  RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
   const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
   const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
   dim3 grid((unsigned)(((long long)H * W + kThreads - 1) / kThreads), B);
-  warp_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(img0, flow, C, H, W, inv_w, inv_h, img1, valid);
+  if (sampler == RMNET_SAMPLER_CUDNN)
+    warp_kernel<0><<<grid, kThreads, 0, (cudaStream_t)stream>>>(img0, flow, C, H, W, inv_w, inv_h, img1, valid);
+  else
+    warp_kernel<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(img0, flow, C, H, W, inv_w, inv_h, img1, valid);
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
 }
 
-int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
+int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
                                float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes,
                                float *att_full, void *workspace, size_t workspace_bytes, void *stream) {
   int rc = check_common(prev_mask, B, K, H, W, bboxes, workspace, workspace_bytes);
   if (rc) return rc;
   RMNET_CHECK_ARG(flow != nullptr, "null flow");
   RMNET_CHECK_ARG(K <= 1024, "K too large");
+  RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);
   const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
   const int per_cta = kThreads * kPixPerThread;
   dim3 grid((unsigned)(((long long)H * W + per_cta - 1) / per_cta), B);
-  warp_bbox_kernel<<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h,
-                                                                prob_threshold, n_pts_threshold,
-                                                                n_bbox_loose_pixels, bboxes, (int *)workspace);
+  if (sampler == RMNET_SAMPLER_CUDNN)
+    warp_bbox_kernel<0><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, prob_threshold,
+                                                                     n_pts_threshold, n_bbox_loose_pixels, bboxes,
+                                                                     (int *)workspace);
+  else
+    warp_bbox_kernel<1><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, prob_threshold,
+                                                                     n_pts_threshold, n_bbox_loose_pixels, bboxes,
+                                                                     (int *)workspace);
   RMNET_LAUNCH_CHECK();
   if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
   return RMNET_OK;

@@ -97,11 +97,11 @@ struct ReadWorkspace {
   int n_splits, nq_pad;
   size_t total;
 };
-enum { READ_MAX_SPLITS = 8 };
-static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N) {
+enum { READ_MAX_SPLITS = 32, KV_TILE = 64, MAX_TILES_PER_SPLIT = 64 };
+static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_splits) {
   ReadWorkspace W;
   W.nq_pad = cdiv(N, 128) * 128;
-  W.n_splits = READ_MAX_SPLITS;
+  W.n_splits = n_splits;
   size_t o = 0;
   W.opart = (float *)((char *)ws + o);
   o = align_up(o + (size_t)W.n_splits * n_obj * RMNET_CV * W.nq_pad * sizeof(float), 1024);
@@ -109,6 +109,31 @@ static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N) {
   o = align_up(o + (size_t)W.n_splits * n_obj * 2 * W.nq_pad * 2 * sizeof(float), 1024);
   W.total = o;
   return W;
+}
+// How many ways the KV axis of every (query tile, object, Cv half) is split.  Host-only information (the cell
+// counts live on the device), so the policy is a function of the bank CAPACITY:
+//   * chain bound: at most MAX_TILES_PER_SPLIT tiles are accumulated back to back on the tensor core.  Its fp32
+//     accumulator truncates instead of rounding, which biases long same-sign sums by ~3e-8 per accumulation
+//     (measured: 1.3e-4 relative over 507 tiles); the split partials are combined by merge.cu in RN fp32.
+//   * wave efficiency: CTAs are one-per-SM heavy, so pick the split count whose CTA total fills whole waves of 148.
+static inline int pick_splits(int n_obj, int N, int q_tile, int cap) {
+  const int base = cdiv(N, q_tile) * n_obj * 2;
+  const int tiles_max = cdiv(cap, KV_TILE);
+  int s_min = cdiv(tiles_max, MAX_TILES_PER_SPLIT);
+  if (s_min < 1) s_min = 1;
+  if (s_min > READ_MAX_SPLITS) s_min = READ_MAX_SPLITS;
+  int s_max = tiles_max / 4;  // keep >= ~4 tiles per split so the per-CTA prologue stays amortised
+  if (s_max < s_min) s_max = s_min;
+  if (s_max > READ_MAX_SPLITS) s_max = READ_MAX_SPLITS;
+  int best = s_min;
+  double best_eff = 0.0;
+  for (int s = s_min; s <= s_max; ++s) {
+    const long long units = (long long)base * s;
+    const long long waves = (units + 147) / 148;
+    const double eff = (double)units / (double)(waves * 148);
+    if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+  }
+  return best;
 }
 
 #ifdef __CUDACC__

@@ -18,14 +18,6 @@ __global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
   if (i < n) reinterpret_cast<int4 *>(rects)[i] = make_int4(0, w - 1, 0, h - 1);
 }
 
-int pick_splits(int n_obj, int N, int q_tile) {
-  // enough CTAs for ~2 per SM on 148 SMs; the KV axis is split flash-decoding style, merged by merge.cu
-  const int base = cdiv(N, q_tile) * n_obj * 2;
-  int s = cdiv(296, base);
-  if (s < 1) s = 1;
-  if (s > READ_MAX_SPLITS) s = READ_MAX_SPLITS;
-  return s;
-}
 }  // namespace
 }  // namespace rmnet
 
@@ -35,14 +27,14 @@ extern "C" {
 int rmnet_has_umma(void) { return umma_supported(64) ? 1 : 0; }
 
 size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells) {
-  (void)cap_cells;
-  if (n_obj <= 0 || h <= 0 || w <= 0) return 0;
-  return read_workspace(nullptr, n_obj, h * w).total;
+  if (n_obj <= 0 || h <= 0 || w <= 0 || cap_cells <= 0) return 0;
+  const int s1 = pick_splits(n_obj, h * w, 64, cap_cells), s2 = pick_splits(n_obj, h * w, 128, cap_cells);
+  return read_workspace(nullptr, n_obj, h * w, s1 > s2 ? s1 : s2).total;
 }
 
 int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
                            const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h, int w,
-                           int elem_format, int precision, int impl, float *mem_val, void *workspace,
+                           int elem_format, int precision, int impl, int stages, float *mem_val, void *workspace,
                            size_t workspace_bytes, void *stream) {
   RMNET_CHECK_ARG(bank && q_key && q_val && mem_val && workspace, "null pointer argument");
   RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
@@ -52,33 +44,32 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
   RMNET_CHECK_ARG(q_rects == nullptr || (uintptr_t)q_rects % 16 == 0, "q_rects must be 16-byte aligned");
   BankLayout L = bank_layout(n_slots, cap_cells);
   if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
-  ReadWorkspace W = read_workspace(workspace, n_obj, h * w);
-  if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
   if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
-  int rc, n_splits;
-  if (impl == RMNET_IMPL_UMMA) {
-    n_splits = pick_splits(n_obj, h * w, 128);
+  RMNET_CHECK_ARG(impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
+  const int n_splits = pick_splits(n_obj, h * w, impl == RMNET_IMPL_UMMA ? 128 : 64, cap_cells);
+  ReadWorkspace W = read_workspace(workspace, n_obj, h * w, n_splits);
+  if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
+  RMNET_CHECK_ARG(stages >= 1 && stages <= 3, "bad stages mask %d", stages);
+  int rc = RMNET_OK;
+  if (!(stages & RMNET_STAGE_PARTIAL)) {
+  } else if (impl == RMNET_IMPL_UMMA)
     rc = launch_memory_read_umma(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
-  } else if (impl == RMNET_IMPL_SIMT) {
-    n_splits = pick_splits(n_obj, h * w, 64);
+  else
     rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
-  } else {
-    set_error("unknown impl %d", impl);
-    return RMNET_E_INVALID;
-  }
-  if (rc) return rc;
+  if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
   return launch_merge(bv, q_val, q_obj_stride ? (q_obj_stride / RMNET_CK) * RMNET_CV : 0, q_rects, n_obj, h, w, n_splits,
                       W, mem_val, st);
 }
 
+extern "C" size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells);
 static size_t reader_scratch_layout(int n, int T, int h, int w, size_t *off_rects, size_t *off_read, int *cap) {
   const int N = h * w;
   *cap = cdiv(T * N, 64) * 64;
   size_t o = align_up(bank_layout(n, *cap).total, 1024);
   *off_rects = o; o = align_up(o + (size_t)n * 16, 1024);
-  *off_read = o; o += read_workspace(nullptr, n, N).total;
+  *off_read = o; o += rmnet_memory_read_workspace_bytes(n, h, w, *cap);
   return o;
 }
 
@@ -115,6 +106,6 @@ int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const fl
     if (rc) return rc;
   }
   return rmnet_bank_memory_read(ws, bank_bytes, n, cap, q_key, q_val, (long long)RMNET_CK * N, rects, n, h, w, elem_format,
-                                precision, impl, mem_val, ws + off_read, workspace_bytes - off_read, stream);
+                                precision, impl, RMNET_STAGE_ALL, mem_val, ws + off_read, workspace_bytes - off_read, stream);
 }
 }

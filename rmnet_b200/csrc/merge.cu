@@ -14,7 +14,7 @@ namespace rmnet {
 namespace {
 
 constexpr int kMergeThreads = 128;
-constexpr int kChPerCta = 32;
+constexpr int kChPerCta = 16;
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_stride, const int *__restrict__ q_rects,
@@ -51,34 +51,30 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   }
   const int n = (cy - qrect.z) * (qrect.y - qrect.x + 1) + (cx - qrect.x);  // compact query index
   const int half = c0 / (RMNET_CV / 2);
-  float wgt[READ_MAX_SPLITS];
+  const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((size_t)o * 2 + half) * nq_pad + n;
+  const size_t ml_stride = (size_t)n_obj * 2 * nq_pad;  // between consecutive splits
   float m_star = Z > 0 ? 0.f : -INFINITY;
-  float2 st[READ_MAX_SPLITS];
-#pragma unroll
-  for (int s = 0; s < READ_MAX_SPLITS; ++s) {
-    if (s < n_splits) {
-      st[s] = __ldg(reinterpret_cast<const float2 *>(ml) + (((size_t)s * n_obj + o) * 2 + half) * nq_pad + n);
-      m_star = fmaxf(m_star, st[s].x);
-    }
-  }
+  for (int s = 0; s < n_splits; ++s) m_star = fmaxf(m_star, __ldg(mlp + s * ml_stride).x);
   float L = Z > 0 ? (float)Z * exp2f(-m_star) : 0.f;
-#pragma unroll
-  for (int s = 0; s < READ_MAX_SPLITS; ++s) {
-    wgt[s] = 0.f;
-    if (s < n_splits) {
-      wgt[s] = (st[s].x == -INFINITY) ? 0.f : exp2f(st[s].x - m_star);
-      L += st[s].y * wgt[s];
-    }
+  for (int s = 0; s < n_splits; ++s) {
+    const float2 st = __ldg(mlp + s * ml_stride);
+    if (st.x != -INFINITY) L += st.y * exp2f(st.x - m_star);
   }
   const float inv_l = 1.0f / L;
-#pragma unroll 4
-  for (int c = c0; c < c0 + kChPerCta; ++c) {
-    float num = 0.f;
+  float num[kChPerCta];
 #pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; ++s)
-      if (s < n_splits && wgt[s] != 0.f) num += __ldg(opart + (((size_t)s * n_obj + o) * RMNET_CV + c) * nq_pad + n) * wgt[s];
-    out[(size_t)c * N] = num * inv_l;
+  for (int k = 0; k < kChPerCta; ++k) num[k] = 0.f;
+  const size_t op_stride = (size_t)n_obj * RMNET_CV * nq_pad;
+  for (int s = 0; s < n_splits; ++s) {
+    const float mx = __ldg(mlp + s * ml_stride).x;
+    if (mx == -INFINITY) continue;  // this split saw no cells: its partial numerators are undefined
+    const float wgt = exp2f(mx - m_star);
+    const float *op = opart + s * op_stride + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
+#pragma unroll
+    for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(__ldg(op + (size_t)k * nq_pad), wgt, num[k]);
   }
+#pragma unroll
+  for (int k = 0; k < kChPerCta; ++k) out[(size_t)(c0 + k) * N] = num[k] * inv_l;
 }
 
 }  // namespace

@@ -60,7 +60,13 @@ def reg_att_map_forward(mask, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loo
     return [att, bboxes]
 
 
-def warp(img0, flow, want_mask=True):
+def default_sampler():
+    """Which bilinear sampler the reference's F.grid_sample(bilinear, zeros, align_corners=True) resolves to on CUDA:
+    cuDNN's spatial-transformer sampler when cuDNN is enabled (torch's default), ATen's own kernel otherwise."""
+    return _lib.SAMPLER_CUDNN if torch.backends.cudnn.enabled else _lib.SAMPLER_ATEN
+
+
+def warp(img0, flow, want_mask=True, sampler=None):
     """RMNet.warp (models/rmnet.py:252-278) -> (img1, mask)."""
     _require(img0, "img0")
     _require(flow, "flow")
@@ -71,13 +77,14 @@ def warp(img0, flow, want_mask=True):
     with torch.cuda.device(dev):
         img1 = torch.empty_like(img0)
         valid = torch.empty_like(img0) if want_mask else None
-        check(lib().rmnet_warp_forward(img0.data_ptr(), flow.data_ptr(), B, C, H, W, img1.data_ptr(),
+        check(lib().rmnet_warp_forward(img0.data_ptr(), flow.data_ptr(), B, C, H, W,
+                                       default_sampler() if sampler is None else sampler, img1.data_ptr(),
                                        valid.data_ptr() if want_mask else None, _stream(dev)), "warp_forward")
     return img1, valid
 
 
 def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64,
-                         want_att=True):
+                         want_att=True, sampler=None):
     """RMNet.get_att_map(prev_mask, flow) (models/rmnet.py:280-287), warp fused into the bbox scan."""
     _require(prev_mask, "prev_mask")
     _require(flow, "flow")
@@ -89,7 +96,8 @@ def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10
         bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
         att = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if want_att else None
         ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
-        check(lib().rmnet_warp_att_map_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W, float(prob_threshold),
+        check(lib().rmnet_warp_att_map_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
+                                               default_sampler() if sampler is None else sampler, float(prob_threshold),
                                                int(n_pts_threshold), int(n_bbox_loose_pixels), bboxes.data_ptr(),
                                                att.data_ptr() if want_att else None, ws.data_ptr(), ws.numel(),
                                                _stream(dev)), "warp_att_map_forward")
@@ -168,7 +176,7 @@ class MemoryBank:
         else:
             self.has_temp = True
 
-    def read(self, q_key, q_val, q_rects, n_obj, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO):
+    def read(self, q_key, q_val, q_rects, n_obj, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, stages=3, out=None):
         """q_key [128,h,w] / q_val [512,h,w] (one frame shared by all objects) or [n,128,h,w] / [n,512,h,w];
         q_rects [n,4] int32 or None (dense) -> mem_val [n,1024,h,w]."""
         _require(q_key, "q_key")
@@ -178,11 +186,12 @@ class MemoryBank:
         if q_rects is not None:
             _require(q_rects, "q_rects", torch.int32)
         with torch.cuda.device(self.device):
-            out = torch.empty((n_obj, 2 * CV, self.h, self.w), dtype=torch.float32, device=self.device)
+            if out is None:
+                out = torch.empty((n_obj, 2 * CV, self.h, self.w), dtype=torch.float32, device=self.device)
             check(lib().rmnet_bank_memory_read(self.ptr, self.nbytes, self.n_slots, self.cap, q_key.data_ptr(),
                                                q_val.data_ptr(), 0 if shared else CK * N,
                                                q_rects.data_ptr() if q_rects is not None else None, n_obj, self.h,
-                                               self.w, self.elem_format, precision, impl, out.data_ptr(), self._ws_ptr,
+                                               self.w, self.elem_format, precision, impl, stages, out.data_ptr(), self._ws_ptr,
                                                self._ws.numel() - 1024, _stream(self.device)), "bank_memory_read")
         return out
 
