@@ -126,8 +126,11 @@ ORACLE_API void oracle_downsample16_nearest(const float *in, int C, int Hp, int 
  *   1 = ne, nw, sw, se : acc = fma(v_se, se, fma(v_sw, sw, fma(v_nw, nw, v_ne * ne)))
  *       cudnnSpatialTfSamplerForward (cuDNN 9.x), which torch dispatches to on CUDA for bilinear / zeros /
  *       align_corners=True when cuDNN is enabled (ATen/native/GridSampler.cpp cond_cudnn_grid_sampler) -- the
- *       reference's default GPU path.  Established empirically on a B200: 0 mismatches in 12 288 samples, every
- *       other of 200+ candidate orders / weight forms mismatches >= 11 % of the samples by 1 ulp.
+ *       reference's default GPU path.  cuDNN also forms the east / south weights as 1 - (west / north weight)
+ *       instead of x - floor(x).  Established empirically on a B200 (tools/warp_probe*.py): 0 mismatches over all
+ *       in-bounds samples incl. the floor == 0 row / column, while every other of 200+ candidate orders / weight
+ *       forms mismatches by 1 ulp somewhere.  (Samples with an out-of-bounds tap can still differ by 1 ulp; they are
+ *       zeroed by the validity mask unless they are within 1e-4 px of the border.)
  * Unnormalisation ((g+1)/2)*(size-1): ATen/native/cuda/GridSampler.cuh:23-31 (= GridSampler.h on CPU).
  * ---------------------------------------------------------------------------------- */
 static inline float oracle_norm_coord(float v, int size, int arith) {
@@ -151,8 +154,12 @@ ORACLE_API int oracle_warp(const float *img0, const float *flow, int C, int H, i
       float ix = ((gx + 1.0f) / 2.0f) * (float)(W - 1);
       float iy = ((gy + 1.0f) / 2.0f) * (float)(H - 1);
       float fx = floorf(ix), fy = floorf(iy);
-      float wx1 = ix - fx, wy1 = iy - fy;              /* distance to west / north */
-      float wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy; /* = 1 - wx1 exactly rounded */
+      float wx0 = (fx + 1.0f) - ix, wy0 = (fy + 1.0f) - iy; /* weight of the west / north tap */
+      float wx1 = ix - fx, wy1 = iy - fy;                   /* ATen: weight of the east / south tap */
+      if (tap_order == 1) { /* cuDNN derives it as 1 - w0, which differs when w0 is inexact (floor == 0 or -1) */
+        wx1 = 1.0f - wx0;
+        wy1 = 1.0f - wy0;
+      }
       float nw = wx0 * wy0, ne = wx1 * wy0, sw = wx0 * wy1, se = wx1 * wy1;
       /* float->int like ATen: static_cast<int>(floor(.)); guard non-finite / huge */
       int x0, y0;

@@ -183,8 +183,11 @@ __device__ __forceinline__ Tap make_tap(int x, int y, float fx, float fy, int H,
   // clamp before the float->int cast (only matters for non-finite / absurd flows; keeps taps out of bounds)
   t.x0 = (flx > -2.0f && flx < (float)W + 1.0f) ? (int)flx : -2;
   t.y0 = (fly > -2.0f && fly < (float)H + 1.0f) ? (int)fly : -2;
-  float wx1 = __fsub_rn(ix, flx), wy1 = __fsub_rn(iy, fly);
-  float wx0 = __fsub_rn(__fadd_rn(flx, 1.0f), ix), wy0 = __fsub_rn(__fadd_rn(fly, 1.0f), iy);
+  const float wx0 = __fsub_rn(__fadd_rn(flx, 1.0f), ix), wy0 = __fsub_rn(__fadd_rn(fly, 1.0f), iy);
+  // east / south weights: ATen uses x - floor(x); cuDNN uses 1 - (west / north weight), which differs by an ulp when
+  // that weight is inexact (floor == 0 or -1).  Established empirically against both samplers on a B200.
+  const float wx1 = ORDER == 1 ? __fsub_rn(ix, flx) : __fsub_rn(1.0f, wx0);
+  const float wy1 = ORDER == 1 ? __fsub_rn(iy, fly) : __fsub_rn(1.0f, wy0);
   t.nw = __fmul_rn(wx0, wy0); t.ne = __fmul_rn(wx1, wy0);
   t.sw = __fmul_rn(wx0, wy1); t.se = __fmul_rn(wx1, wy1);
   const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
@@ -243,7 +246,7 @@ warp_kernel(const float *__restrict__ img0, const float *__restrict__ flow, int 
 }
 
 // ---- fused warp + threshold + bbox: grid (pixel tiles, B) ----------------------------------------
-constexpr int kPixPerThread = 4;
+constexpr int kPixPerThread = 2;
 template <int ORDER>
 __global__ void __launch_bounds__(kThreads)
 warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
@@ -279,8 +282,9 @@ warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ 
     for (int p = 0; p < kPixPerThread; ++p) {
       if (live[p] && sample_tap<ORDER>(plane, taps[p], H, W) >= thr) acc.hit(px[p], py[p]);
     }
+    if (!__any_sync(0xffffffffu, acc.cnt > 0)) continue;  // background warp: nothing to reduce for this channel
     acc.warp_reduce();
-    if (lane == 0 && acc.cnt > 0) {
+    if (lane == 0) {
       atomicAdd(&s_acc[i * 5 + 0], acc.cnt);
       atomicMax(&s_acc[i * 5 + 1], 32767 - acc.xmin);
       atomicMax(&s_acc[i * 5 + 2], acc.xmax);

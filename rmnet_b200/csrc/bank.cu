@@ -15,23 +15,27 @@ namespace {
 
 constexpr int kCellsPerCta = 64;
 constexpr int kPackThreads = 256;
-constexpr int kKRowStride = RMNET_CK + 4;  // ushorts; keeps 8-byte row alignment, spreads banks
+constexpr int kChunk = 128;                          // channels per CTA: blockIdx.y = 0 -> keys, 1..4 -> value chunks
+constexpr int kKRowStride = RMNET_CK + 4;            // ushorts; keeps 8-byte row alignment, spreads banks
+constexpr int kGroups = kPackThreads / kCellsPerCta; // 4 channel groups; lanes run along cells (coalesced gathers)
+constexpr int kPerThread = kChunk / kGroups;         // 32 channels per thread
 
+template <int FMT>
 __global__ void __launch_bounds__(kPackThreads)
 bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_stride, long long k_ch_stride,
                  const float *__restrict__ v4, long long v_obj_stride, long long v_ch_stride,
-                 const int *__restrict__ rects, int h, int w, int fmt) {
+                 const int *__restrict__ rects, int h, int w) {
   __shared__ __align__(16) uint16_t s_hi[kCellsPerCta][kKRowStride];
   __shared__ __align__(16) uint16_t s_lo[kCellsPerCta][kKRowStride];
-  __shared__ float s_vsum[RMNET_CV];
+  __shared__ float s_vsum[kChunk];
 
-  const int o = blockIdx.y;
+  const int o = blockIdx.z;
   const int4 rect = __ldg(reinterpret_cast<const int4 *>(rects) + o);
   const int r = rect_cells(rect);
   int *meta = bank.meta + o * 8;
   const int base = meta[META_CELLS_C];
   const bool overflow = base + r > bank.cap;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
     meta[META_CELLS_T] = overflow ? 0 : r;
     meta[META_ZEROS_T] = overflow ? h * w : h * w - r;
     meta[META_FRAMES_T] = 1;
@@ -41,52 +45,60 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
   if (i0 >= r || overflow) return;
   const int cnt = min(kCellsPerCta, r - i0);
 
-  for (int c = threadIdx.x; c < RMNET_CV; c += kPackThreads) s_vsum[c] = 0.f;
-
-  const int li = threadIdx.x & (kCellsPerCta - 1);  // cell within the tile (lanes run along cells: coalesced reads)
-  const int cg = threadIdx.x / kCellsPerCta;        // channel group 0..3
+  const int li = threadIdx.x & (kCellsPerCta - 1);  // cell within the tile
+  const int cg = threadIdx.x / kCellsPerCta;        // channel group
   const bool live = li < cnt;
   const int pos = live ? rect_pos(rect, i0 + li, w) : 0;
 
-  // ---- keys: gather -> split -> transpose through smem -> 256 B position-major rows
-  const float *kp = k4 + (long long)o * k_obj_stride + pos;
-#pragma unroll 4
-  for (int c = cg; c < RMNET_CK; c += kPackThreads / kCellsPerCta) {
-    float x = live ? __ldg(kp + (long long)c * k_ch_stride) : 0.f;
-    uint16_t hi, lo;
-    split16(x, fmt, hi, lo);
-    s_hi[li][c] = hi;
-    s_lo[li][c] = lo;
-  }
-  __syncthreads();
-  {
+  if (blockIdx.y == 0) {
+    // ---- keys: gather -> split -> transpose through smem -> 256 B position-major rows
+    const float *kp = k4 + (long long)o * k_obj_stride + pos;
+    float x[kPerThread];
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) x[k] = live ? __ldg(kp + (long long)(cg + kGroups * k) * k_ch_stride) : 0.f;
+#pragma unroll
+    for (int k = 0; k < kPerThread; ++k) {
+      uint16_t hi, lo;
+      split16(x[k], FMT, hi, lo);
+      s_hi[li][cg + kGroups * k] = hi;
+      s_lo[li][cg + kGroups * k] = lo;
+    }
+    __syncthreads();
     const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
     for (int row = wrp; row < cnt; row += kPackThreads / 32) {
       const size_t g = ((size_t)o * bank.cap + base + i0 + row) * RMNET_CK + lane * 4;
       *reinterpret_cast<uint2 *>(bank.khi + g) = *reinterpret_cast<const uint2 *>(&s_hi[row][lane * 4]);
       *reinterpret_cast<uint2 *>(bank.klo + g) = *reinterpret_cast<const uint2 *>(&s_lo[row][lane * 4]);
     }
+    return;
   }
 
-  // ---- values: gather -> split -> channel-major rows (lanes along cells), plus per-channel sums
+  // ---- values: gather -> split -> channel-major rows (lanes along cells), plus per-channel sums of the chunk
+  const int cbase = (blockIdx.y - 1) * kChunk;
+  if (threadIdx.x < kChunk) s_vsum[threadIdx.x] = 0.f;
+  __syncthreads();
   const float *vp = v4 + (long long)o * v_obj_stride + pos;
   const size_t vrow0 = (size_t)o * RMNET_CV * bank.cap + base + i0 + li;
-  for (int c = cg; c < RMNET_CV; c += kPackThreads / kCellsPerCta) {
-    float x = live ? __ldg(vp + (long long)c * v_ch_stride) : 0.f;
+  float x[kPerThread];
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) x[k] = live ? __ldg(vp + (long long)(cbase + cg + kGroups * k) * v_ch_stride) : 0.f;
+#pragma unroll
+  for (int k = 0; k < kPerThread; ++k) {
+    const int c = cbase + cg + kGroups * k;
     if (live) {
       uint16_t hi, lo;
-      split16(x, fmt, hi, lo);
+      split16(x[k], FMT, hi, lo);
       bank.vhi[vrow0 + (size_t)c * bank.cap] = hi;
       bank.vlo[vrow0 + (size_t)c * bank.cap] = lo;
     }
-    float s = x;
+    float sum = x[k];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&s_vsum[c], s);
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&s_vsum[c - cbase], sum);  // two warps share a channel
   }
   __syncthreads();
-  float *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
-  for (int c = threadIdx.x; c < RMNET_CV; c += kPackThreads) atomicAdd(vs_t + c, s_vsum[c]);
+  if (threadIdx.x < kChunk)
+    atomicAdd(bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV + cbase + threadIdx.x, s_vsum[threadIdx.x]);
 }
 
 // `keys = this_keys` (models/rmnet.py:424-426): the temporary frame becomes permanent.
@@ -140,9 +152,11 @@ int rmnet_bank_memorize(void *bank, size_t bank_bytes, int n_slots, int cap_cell
   BankView bv = bank_view(bank, n_slots, cap_cells);
   // vsum of the temporary frame restarts from zero
   RMNET_CUDA(cudaMemsetAsync(bv.vsum + (size_t)n_slots * RMNET_CV, 0, (size_t)n_slots * RMNET_CV * sizeof(float), st));
-  dim3 grid(cdiv(h * w, kCellsPerCta), n_obj);
-  bank_pack_kernel<<<grid, kPackThreads, 0, st>>>(bv, k4, k_obj_stride, k_ch_stride, v4, v_obj_stride, v_ch_stride,
-                                                  rects, h, w, elem_format);
+  dim3 grid(cdiv(h * w, kCellsPerCta), 1 + RMNET_CV / kChunk, n_obj);
+  if (elem_format == 0)
+    bank_pack_kernel<0><<<grid, kPackThreads, 0, st>>>(bv, k4, k_obj_stride, k_ch_stride, v4, v_obj_stride, v_ch_stride, rects, h, w);
+  else
+    bank_pack_kernel<1><<<grid, kPackThreads, 0, st>>>(bv, k4, k_obj_stride, k_ch_stride, v4, v_obj_stride, v_ch_stride, rects, h, w);
   RMNET_LAUNCH_CHECK();
   if (commit) {
     bank_commit_kernel<<<n_obj, 128, 0, st>>>(bv, n_obj);

@@ -110,19 +110,22 @@ static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_spl
   W.total = o;
   return W;
 }
-// How many ways the KV axis of every (query tile, object, Cv half) is split.  Host-only information (the cell
-// counts live on the device), so the policy is a function of the bank CAPACITY:
+// How many ways the KV axis of every (query tile, object, Cv half) MAY be split (grid.z / 2).  The cell counts live
+// on the device, so the host policy is a function of the bank CAPACITY and only an upper bound: on the device a
+// split covers  per = max(MIN_TILES_PER_SPLIT, ceil(n_tiles / n_splits))  tiles and surplus CTAs exit at once.
 //   * chain bound: at most MAX_TILES_PER_SPLIT tiles are accumulated back to back on the tensor core.  Its fp32
 //     accumulator truncates instead of rounding, which biases long same-sign sums by ~3e-8 per accumulation
 //     (measured: 1.3e-4 relative over 507 tiles); the split partials are combined by merge.cu in RN fp32.
-//   * wave efficiency: CTAs are one-per-SM heavy, so pick the split count whose CTA total fills whole waves of 148.
+//   * wave efficiency: CTAs are one-per-SM heavy, so among split counts that keep >= 16 tiles per CTA at full
+//     capacity pick the one whose CTA total fills whole waves of 148 SMs best.
+enum { MIN_TILES_PER_SPLIT = 8 };
 static inline int pick_splits(int n_obj, int N, int q_tile, int cap) {
   const int base = cdiv(N, q_tile) * n_obj * 2;
   const int tiles_max = cdiv(cap, KV_TILE);
   int s_min = cdiv(tiles_max, MAX_TILES_PER_SPLIT);
   if (s_min < 1) s_min = 1;
   if (s_min > READ_MAX_SPLITS) s_min = READ_MAX_SPLITS;
-  int s_max = tiles_max / 4;  // keep >= ~4 tiles per split so the per-CTA prologue stays amortised
+  int s_max = tiles_max / 16;
   if (s_max < s_min) s_max = s_min;
   if (s_max > READ_MAX_SPLITS) s_max = READ_MAX_SPLITS;
   int best = s_min;
@@ -135,6 +138,17 @@ static inline int pick_splits(int n_obj, int N, int q_tile, int cap) {
   }
   return best;
 }
+#if defined(__CUDACC__)
+// device-side resolution of the split -> [tile_begin, tile_begin + n_it) for `count` stored cells
+__device__ __forceinline__ void split_range(int count, int n_splits, int split, int &tile_begin, int &n_it) {
+  const int n_tiles = (count + KV_TILE - 1) / KV_TILE;
+  int per = (n_tiles + n_splits - 1) / n_splits;
+  if (per < MIN_TILES_PER_SPLIT) per = MIN_TILES_PER_SPLIT;
+  tile_begin = split * per;
+  n_it = min(n_tiles, tile_begin + per) - tile_begin;
+  if (n_it < 0) n_it = 0;
+}
+#endif
 
 #ifdef __CUDACC__
 // 16-bit hi/lo split of an fp32 value.  fmt 0 = bf16, 1 = fp16.  x ~= hi + lo with |err| <= 2^-17|x| (bf16).

@@ -42,9 +42,9 @@ memory_read_simt_kernel(BankView bank, const float *__restrict__ q_key, long lon
 
   const int *meta = bank.meta + o * 8;
   const int count = meta[META_CELLS_C] + meta[META_CELLS_T];
-  const int n_tiles = (count + MT - 1) / MT;
-  const int per = (n_tiles + n_splits - 1) / n_splits;
-  const int tile_begin = split * per, tile_end = min(n_tiles, tile_begin + per);
+  int tile_begin, n_it;
+  split_range(count, n_splits, split, tile_begin, n_it);
+  const int tile_end = tile_begin + n_it;
 
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const float scale = 1.4426950408889634f / sqrtf((float)RMNET_CK);

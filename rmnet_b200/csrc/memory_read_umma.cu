@@ -123,13 +123,38 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
                  "r"(r[o + 12]), "r"(r[o + 13]), "r"(r[o + 14]), "r"(r[o + 15])                                       \
                : "memory")
 
-// pack two fp32 into one 32-bit word of 16-bit values (element 0 in the low half) + the residual planes
-__device__ __forceinline__ void split_pack2(float x0, float x1, int fmt, uint32_t &hi, uint32_t &lo) {
-  uint16_t h0, l0, h1, l1;
-  split16(x0, fmt, h0, l0);
-  split16(x1, fmt, h1, l1);
-  hi = (uint32_t)h0 | ((uint32_t)h1 << 16);
-  lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+#define TMEM_ST8(addr, r, o)                                                                              \
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"                   \
+               ::"r"(addr), "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]),    \
+                 "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])                                              \
+               : "memory")
+
+__device__ __forceinline__ float ex2_approx(float x) {  // MUFU.EX2, rel. error 2^-22; ex2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Two fp32 -> one 32-bit word of 16-bit values (x0 in the low half) and the word of the residuals x - hi.
+// One cvt.rn.{bf16x2,f16x2}.f32 per word; the residual subtraction is exact in fp32.
+template <int FMT, bool LO>
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+  if (FMT == 0) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    if (LO) {
+      const float r0 = x0 - __uint_as_float(hi << 16), r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+      __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+      lo = *reinterpret_cast<uint32_t *>(&l);
+    }
+  } else {
+    __half2 h = __floats2half2_rn(x0, x1);
+    hi = *reinterpret_cast<uint32_t *>(&h);
+    if (LO) {
+      const float2 f = __half22float2(h);
+      __half2 l = __floats2half2_rn(x0 - f.x, x1 - f.y);
+      lo = *reinterpret_cast<uint32_t *>(&l);
+    }
+  }
 }
 
 struct Barriers {
@@ -138,11 +163,12 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+template <int FMT, bool USE_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
                         const int *__restrict__ bank_meta, const float *__restrict__ q_key, long long q_obj_stride,
-                        const int *__restrict__ q_rects, int h, int w, int fmt, int use_lo, int n_splits,
+                        const int *__restrict__ q_rects, int h, int w, int n_splits,
                         float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj,
                         float *__restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
@@ -161,10 +187,17 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
 
   const int *meta = bank_meta + o * 8;
   const int count = meta[META_CELLS_C] + meta[META_CELLS_T];
-  const int n_tiles = (count + MT - 1) / MT;
-  const int per = (n_tiles + n_splits - 1) / n_splits;
-  const int tile_begin = split * per;
-  const int n_it = max(0, min(n_tiles, tile_begin + per) - tile_begin);
+  int tile_begin, n_it;
+  split_range(count, n_splits, split, tile_begin, n_it);
+  if (n_it == 0) {  // surplus split (the grid is sized for the bank capacity): publish "saw nothing" and leave
+    if (threadIdx.x >= 128) {
+      float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)split * n_obj + o) * 2 + half) * nq_pad + q0 + (threadIdx.x - 128);
+      *dst = make_float2(-INFINITY, 0.f);
+    }
+    return;
+  }
+  constexpr int fmt = FMT;
+  constexpr bool use_lo = USE_LO;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -296,10 +329,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         for (int j = 0; j < 16; ++j) {
           const float x0 = live ? __ldg(qp + (long long)(c0 + 2 * j) * N) : 0.f;
           const float x1 = live ? __ldg(qp + (long long)(c0 + 2 * j + 1) * N) : 0.f;
-          split_pack2(x0, x1, fmt, hi[j], lo[j]);
+          lo[j] = 0;
+          split_pack2<FMT, USE_LO>(x0, x1, hi[j], lo[j]);
         }
         TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
-        TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
+        if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
       }
       tc_wait_st();
       tc_fence_before();
@@ -322,15 +356,18 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
 #pragma unroll
         for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
       }
-      const int valid = count - (tile_begin + it) * MT;  // columns >= valid are beyond the stored cells
-      float mx = -INFINITY;
+      const int valid = count - (tile_begin + it) * MT;  // columns >= valid are beyond the stored cells (last tile only)
+      if (valid < MT) {
 #pragma unroll
-      for (int j = 0; j < MT; ++j) {
-        float t = __uint_as_float(sr[j]) * scale;
-        t = (j < valid) ? t : -INFINITY;
-        sr[j] = __float_as_uint(t);
-        mx = fmaxf(mx, t);
+        for (int j = 0; j < MT; ++j) if (j >= valid) sr[j] = 0xff800000u;  // -inf
       }
+      float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
+#pragma unroll
+      for (int j = 2; j < MT; j += 2) {
+        mx0 = fmaxf(mx0, __uint_as_float(sr[j]));
+        mx1 = fmaxf(mx1, __uint_as_float(sr[j + 1]));
+      }
+      const float mx = fmaxf(mx0, mx1) * scale;  // scale > 0: max commutes with the scaling
       if (it == 0) {
         m_ref = (mx == -INFINITY) ? 0.f : mx;
       } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
@@ -354,27 +391,26 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         l_sum *= f;
         m_ref = m_new;
       }
-      // P = 2^(t - m_ref), split into 16-bit hi/lo planes, packed two cells per TMEM column over the S buffer
-      uint32_t ph[MT / 2], pl[MT / 2];
+      // P = 2^(s*scale - m_ref): one FFMA + one MUFU per element, then the 16-bit hi/lo split (packed cvt), stored
+      // two cells per TMEM column over the S buffer: hi plane in columns [0,32), lo plane in [32,64)
+      const float neg_m = -m_ref;
+      float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < MT / 2; ++j) {
-        const float p0 = exp2f(__uint_as_float(sr[2 * j]) - m_ref);
-        const float p1 = exp2f(__uint_as_float(sr[2 * j + 1]) - m_ref);
-        uint16_t h0, l0, h1, l1;
-        split16(p0, fmt, h0, l0);
-        split16(p1, fmt, h1, l1);
-        if (!use_lo) { l0 = 0; l1 = 0; }
-        // the denominator sums exactly what the tensor core will multiply (hi + lo), so num / den stays a convex combination
-        l_sum += (cvt16(h0, fmt) + cvt16(l0, fmt)) + (cvt16(h1, fmt) + cvt16(l1, fmt));
-        ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+      for (int c = 0; c < MT; c += 16) {
+        uint32_t ph[8], pl[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j]), scale, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j + 1]), scale, neg_m));
+          l0 += p0;
+          l1 += p1;
+          pl[j] = 0;
+          split_pack2<FMT, USE_LO>(p0, p1, ph[j], pl[j]);
+        }
+        TMEM_ST8(s_addr + c / 2, ph, 0);
+        if (USE_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
       }
-      TMEM_ST16(s_addr, ph, 0);
-      TMEM_ST16(s_addr + 16, ph, 16);
-      if (use_lo) {
-        TMEM_ST16(s_addr + 32, pl, 0);
-        TMEM_ST16(s_addr + 48, pl, 16);
-      }
+      l_sum += l0 + l1;
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->p_full[b]));
@@ -459,11 +495,21 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
   if ((rc = make_map(&mkl, bank.klo, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
   if ((rc = make_map(&mvh, bank.vhi, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
   if ((rc = make_map(&mvl, bank.vlo, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
-  RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
   dim3 grid(cdiv(h * w, QT), n_obj, 2 * n_splits);
-  memory_read_umma_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, q_rects,
-                                                              h, w, fmt, precision == RMNET_PREC_SPLIT3 ? 1 : 0, n_splits,
-                                                              W.opart, W.ml, W.nq_pad, n_obj, g_dbg);
+  const bool lo = precision == RMNET_PREC_SPLIT3;
+#define RMNET_LAUNCH_UMMA(F, L)                                                                                          \
+  do {                                                                                                                   \
+    RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                    (int)SMEM_BYTES));                                                                   \
+    memory_read_umma_kernel<F, L><<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, \
+                                                                      q_rects, h, w, n_splits, W.opart, W.ml, W.nq_pad, \
+                                                                      n_obj, g_dbg);                                     \
+  } while (0)
+  if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
+  else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);
+  else if (lo) RMNET_LAUNCH_UMMA(1, true);
+  else RMNET_LAUNCH_UMMA(1, false);
+#undef RMNET_LAUNCH_UMMA
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
 }
