@@ -106,6 +106,21 @@ RMNET_API int rmnet_warp_att_map_forward(const float *prev_mask, const float *fl
                                size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Region descriptors of one frame in ONE launch: bounding boxes + /16 cell rectangles, straight from the
+ * UNPADDED soft masks -- replaces pad_divide_by (utils/helpers.py:105-124) + get_att_map + F.interpolate(1/16):
+ *   flow == NULL, bbox_in_padded_frame = 1 : the memorise side, models/rmnet.py:212 + :244-245 (box of the zero-padded
+ *       mask, in padded coordinates);
+ *   flow != NULL, bbox_in_padded_frame = 0 : the segment side, :431 (warp + box in raw coordinates) + :307 + :356.
+ *   pad_* = pad_divide_by amounts (lw, uw, lh, uh); bboxes [B,K,4]; cell_rects [B,K,4] (cx0,cx1,cy0,cy1), channel 0
+ *   and empty boxes -> (0,-1,0,-1); workspace as rmnet_reg_att_map_forward.
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, int K, int H, int W,
+                                           int sampler, float prob_threshold, int n_pts_threshold,
+                                           int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t, int pad_b,
+                                           int bbox_in_padded_frame, int *bboxes, int *cell_rects,
+                                           void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Low-resolution cell rectangles: the closed form of
  *   F.interpolate(pad(att_map), scale_factor=1/16)             (models/rmnet.py:245, :307+:356)
  * for a rectangular att_map:  cx in [ceil((x0+pad_l)/16), floor((x1+pad_l)/16)], same for y.

@@ -47,31 +47,57 @@ __device__ __forceinline__ void ws_accumulate(int *ws, const BoxAcc &a) {
   }
 }
 
+// How the raw scan result of one channel becomes the outputs.  The scan runs on the UNPADDED mask; `off_*` shifts
+// it into the frame the reference computes the box in (the zero-padded frame on the memorise path,
+// models/rmnet.py:212+:244; the raw frame on the segment path, :431), Hf x Wf is that frame's size.
+// rects (nullable): the /16 cell rectangle of the box, i.e. pad (:307) + F.interpolate(1/16) (:245, :356) in closed form.
+struct BoxFinalize {
+  int Hf, Wf, off_x, off_y;  // frame of the bbox
+  int n_pts_threshold, loose, force_full;
+  int *rects;                // [B,K,4] or nullptr
+  int rect_pad_l, rect_pad_t, cell_h, cell_w;
+};
+
+__device__ __forceinline__ void write_rect(const BoxFinalize &f, long long ch, const int4 bb, bool empty) {
+  if (!f.rects) return;
+  int4 r;
+  r.x = max(0, (bb.x + f.rect_pad_l + 15) >> 4);
+  r.y = min(f.cell_w - 1, (bb.y + f.rect_pad_l) >> 4);
+  r.z = max(0, (bb.z + f.rect_pad_t + 15) >> 4);
+  r.w = min(f.cell_h - 1, (bb.w + f.rect_pad_t) >> 4);
+  if (empty || r.x > r.y || r.z > r.w) r = make_int4(0, -1, 0, -1);
+  reinterpret_cast<int4 *>(f.rects)[ch] = r;
+}
+
 // reg_att_map_generator.cu:55-77 -- loosen / clamp, or full frame when too few points.
 // Reads AND clears the workspace accumulators (self-cleaning).
-__device__ __forceinline__ void finalize_channel(int *ws, int *bbox, int H, int W, int n_pts_threshold,
-                                                 int loose) {
+__device__ __forceinline__ void finalize_channel(int *ws, int *bboxes, long long ch, const BoxFinalize &f) {
   int cnt = atomicExch(ws + 0, 0);
-  int xmin = 32767 - atomicExch(ws + 1, 0);
-  int xmax = atomicExch(ws + 2, 0);
-  int ymin = 32767 - atomicExch(ws + 3, 0);
-  int ymax = atomicExch(ws + 4, 0);
+  int xmin = 32767 - atomicExch(ws + 1, 0) + f.off_x;
+  int xmax = atomicExch(ws + 2, 0) + f.off_x;
+  int ymin = 32767 - atomicExch(ws + 3, 0) + f.off_y;
+  int ymax = atomicExch(ws + 4, 0) + f.off_y;
   int4 r;
-  if (cnt < n_pts_threshold) {
-    r = make_int4(0, W - 1, 0, H - 1);
+  if (cnt < f.n_pts_threshold || f.force_full) {
+    r = make_int4(0, f.Wf - 1, 0, f.Hf - 1);
   } else {
-    r.x = xmin <= loose ? 0 : xmin - loose;
-    r.y = xmax + loose >= W ? W - 1 : xmax + loose;
-    r.z = ymin <= loose ? 0 : ymin - loose;
-    r.w = ymax + loose >= H ? H - 1 : ymax + loose;
+    r.x = xmin <= f.loose ? 0 : xmin - f.loose;
+    r.y = xmax + f.loose >= f.Wf ? f.Wf - 1 : xmax + f.loose;
+    r.z = ymin <= f.loose ? 0 : ymin - f.loose;
+    r.w = ymax + f.loose >= f.Hf ? f.Hf - 1 : ymax + f.loose;
   }
-  *reinterpret_cast<int4 *>(bbox) = r;  // bboxes are [.,4] i32, 16 B aligned per entry
+  reinterpret_cast<int4 *>(bboxes)[ch] = r;  // bboxes are [.,4] i32, 16 B aligned per entry
+  write_rect(f, ch, r, false);
+}
+__device__ __forceinline__ void finalize_channel0(int *bboxes, long long ch, const BoxFinalize &f) {
+  reinterpret_cast<int4 *>(bboxes)[ch] = make_int4(0, 0, 0, 0);  // channel 0 keeps the zero fill (.cu:104)
+  write_rect(f, ch, make_int4(0, 0, 0, 0), true);               // its att_map is all zero
 }
 
 // ---- plain generator: grid (chunks, K-1, B) ----------------------------------------------------
 template <int VEC>
 __global__ void __launch_bounds__(kThreads)
-bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr, int n_pts_threshold, int loose,
+bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr, BoxFinalize fin,
                  int elems_per_cta, int *__restrict__ bboxes, int *__restrict__ ws) {
   const int b = blockIdx.z, i = blockIdx.y + 1;
   const long long n_pixels = (long long)H * W;
@@ -134,9 +160,9 @@ bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr,
   __syncthreads();
   if (s_last && threadIdx.x == 0) {
     __threadfence();
-    finalize_channel(ws_ch, bboxes + ((long long)b * K + i) * 4, H, W, n_pts_threshold, loose);
+    finalize_channel(ws_ch, bboxes, (long long)b * K + i, fin);
     atomicExch(ws_ch + 5, 0);
-    if (i == 1) *reinterpret_cast<int4 *>(bboxes + (long long)b * K * 4) = make_int4(0, 0, 0, 0);  // channel 0 (:104 zeros)
+    if (i == 1) finalize_channel0(bboxes, (long long)b * K, fin);
   }
 }
 
@@ -250,7 +276,7 @@ constexpr int kPixPerThread = 2;
 template <int ORDER>
 __global__ void __launch_bounds__(kThreads)
 warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
-                 float inv_w, float inv_h, float thr, int n_pts_threshold, int loose, int *__restrict__ bboxes,
+                 float inv_w, float inv_h, float thr, BoxFinalize fin, int *__restrict__ bboxes,
                  int *__restrict__ ws) {
   extern __shared__ int s_acc[];  // [K][5] CTA accumulators (zero identity, mins inverted)
   __shared__ bool s_last;
@@ -314,9 +340,8 @@ warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ 
   if (s_last) {
     __threadfence();
     for (int i = threadIdx.x; i < K; i += kThreads) {
-      int *bb = bboxes + ((long long)b * K + i) * 4;
-      if (i == 0) *reinterpret_cast<int4 *>(bb) = make_int4(0, 0, 0, 0);
-      else finalize_channel(ws_b + i * kWsIntsPerChannel, bb, H, W, n_pts_threshold, loose);
+      if (i == 0) finalize_channel0(bboxes, (long long)b * K, fin);
+      else finalize_channel(ws_b + i * kWsIntsPerChannel, bboxes, (long long)b * K + i, fin);
     }
     if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);
   }
@@ -375,31 +400,83 @@ size_t rmnet_reg_att_map_workspace_bytes(int B, int K) {
   return (size_t)B * (K + 1) * kWsIntsPerChannel * sizeof(int);
 }
 
-int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,
-                              int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes, float *att_full,
-                              void *workspace, size_t workspace_bytes, void *stream) {
-  int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
-  if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+static int launch_scan(const float *mask, int B, int K, int H, int W, float thr, const BoxFinalize &fin, int *bboxes,
+                       void *workspace, cudaStream_t st) {
   const long long n_pixels = (long long)H * W;
   const bool vec = n_pixels % 4 == 0 && W >= 4 && ((uintptr_t)mask % 16 == 0);
-  // ~2 CTAs per SM per channel-batch: each CTA streams a contiguous chunk (multiple of the 4096-float tile)
-  long long want_ctas = 148LL * 4;
+  // ~8 CTAs per SM over all channels: each CTA streams a contiguous chunk (multiple of the 4096-float tile)
+  long long want_ctas = 148LL * 8;
   long long per_channel = (want_ctas + (long long)(K - 1) * B - 1) / ((long long)(K - 1) * B);
   if (per_channel < 1) per_channel = 1;
   long long elems = (n_pixels + per_channel - 1) / per_channel;
   elems = (elems + 4095) / 4096 * 4096;
   const int chunks = (int)((n_pixels + elems - 1) / elems);
   dim3 grid(chunks, K - 1, B);
-  if (vec)
-    bbox_scan_kernel<4><<<grid, kThreads, 0, st>>>(mask, K, H, W, prob_threshold, n_pts_threshold,
-                                                   n_bbox_loose_pixels, (int)elems, bboxes, (int *)workspace);
-  else
-    bbox_scan_kernel<1><<<grid, kThreads, 0, st>>>(mask, K, H, W, prob_threshold, n_pts_threshold,
-                                                   n_bbox_loose_pixels, (int)elems, bboxes, (int *)workspace);
+  if (vec) bbox_scan_kernel<4><<<grid, kThreads, 0, st>>>(mask, K, H, W, thr, fin, (int)elems, bboxes, (int *)workspace);
+  else bbox_scan_kernel<1><<<grid, kThreads, 0, st>>>(mask, K, H, W, thr, fin, (int)elems, bboxes, (int *)workspace);
   RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
+static int launch_warp_scan(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler, float thr,
+                            const BoxFinalize &fin, int *bboxes, void *workspace, cudaStream_t st) {
+  const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
+  const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
+  const int per_cta = kThreads * kPixPerThread;
+  dim3 grid((unsigned)(((long long)H * W + per_cta - 1) / per_cta), B);
+  if (sampler == RMNET_SAMPLER_CUDNN)
+    warp_bbox_kernel<0><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin, bboxes,
+                                                                     (int *)workspace);
+  else
+    warp_bbox_kernel<1><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin, bboxes,
+                                                                     (int *)workspace);
+  RMNET_LAUNCH_CHECK();
+  return RMNET_OK;
+}
+
+int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,
+                              int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes, float *att_full,
+                              void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, nullptr, 0, 0, 0, 0};
+  if ((rc = launch_scan(mask, B, K, H, W, prob_threshold, fin, bboxes, workspace, st))) return rc;
   if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
   return RMNET_OK;
+}
+
+int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, int K, int H, int W, int sampler,
+                                 float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
+                                 int pad_t, int pad_b, int bbox_in_padded_frame, int *bboxes, int *cell_rects,
+                                 void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
+  if (rc) return rc;
+  RMNET_CHECK_ARG(pad_l >= 0 && pad_r >= 0 && pad_t >= 0 && pad_b >= 0, "negative padding");
+  RMNET_CHECK_ARG((H + pad_t + pad_b) % 16 == 0 && (W + pad_l + pad_r) % 16 == 0, "padded frame must be a multiple of 16");
+  RMNET_CHECK_ARG(H + pad_t + pad_b <= 32767 && W + pad_l + pad_r <= 32767, "padded frame too large");
+  RMNET_CHECK_ARG(cell_rects == nullptr || (uintptr_t)cell_rects % 16 == 0, "cell_rects must be 16-byte aligned");
+  RMNET_CHECK_ARG(flow == nullptr || sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
+  RMNET_CHECK_ARG(K <= 1024, "K too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  BoxFinalize fin;
+  const bool padded = bbox_in_padded_frame != 0;
+  fin.Hf = padded ? H + pad_t + pad_b : H;
+  fin.Wf = padded ? W + pad_l + pad_r : W;
+  fin.off_x = padded ? pad_l : 0;
+  fin.off_y = padded ? pad_t : 0;
+  fin.n_pts_threshold = n_pts_threshold;
+  fin.loose = n_bbox_loose_pixels;
+  // zero padding passes a threshold <= 0: every padded pixel is a point, the loosened box is the whole frame
+  fin.force_full = (padded && prob_threshold <= 0.0f && (pad_l | pad_r | pad_t | pad_b) &&
+                    (long long)fin.Hf * fin.Wf >= n_pts_threshold) ? 1 : 0;
+  fin.rects = cell_rects;
+  fin.rect_pad_l = padded ? 0 : pad_l;
+  fin.rect_pad_t = padded ? 0 : pad_t;
+  fin.cell_h = (H + pad_t + pad_b) / 16;
+  fin.cell_w = (W + pad_l + pad_r) / 16;
+  if (flow) return launch_warp_scan(mask, flow, B, K, H, W, sampler, prob_threshold, fin, bboxes, workspace, st);
+  return launch_scan(mask, B, K, H, W, prob_threshold, fin, bboxes, workspace, st);
 }
 
 int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H, int W, int sampler, float *img1,
@@ -427,19 +504,8 @@ int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B,
   RMNET_CHECK_ARG(K <= 1024, "K too large");
   RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
   cudaStream_t st = (cudaStream_t)stream;
-  const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);
-  const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
-  const int per_cta = kThreads * kPixPerThread;
-  dim3 grid((unsigned)(((long long)H * W + per_cta - 1) / per_cta), B);
-  if (sampler == RMNET_SAMPLER_CUDNN)
-    warp_bbox_kernel<0><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, prob_threshold,
-                                                                     n_pts_threshold, n_bbox_loose_pixels, bboxes,
-                                                                     (int *)workspace);
-  else
-    warp_bbox_kernel<1><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, prob_threshold,
-                                                                     n_pts_threshold, n_bbox_loose_pixels, bboxes,
-                                                                     (int *)workspace);
-  RMNET_LAUNCH_CHECK();
+  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, nullptr, 0, 0, 0, 0};
+  if ((rc = launch_warp_scan(prev_mask, flow, B, K, H, W, sampler, prob_threshold, fin, bboxes, workspace, st))) return rc;
   if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
   return RMNET_OK;
 }

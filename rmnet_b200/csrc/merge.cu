@@ -14,7 +14,7 @@ namespace rmnet {
 namespace {
 
 constexpr int kMergeThreads = 128;
-constexpr int kChPerCta = 16;
+constexpr int kChPerCta = 8;
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_stride, const int *__restrict__ q_rects,
@@ -53,26 +53,42 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   const int half = c0 / (RMNET_CV / 2);
   const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((size_t)o * 2 + half) * nq_pad + n;
   const size_t ml_stride = (size_t)n_obj * 2 * nq_pad;  // between consecutive splits
+  // pass 1: statistics of every split (8 B each, independent loads), reference max, denominator
   float m_star = Z > 0 ? 0.f : -INFINITY;
-  for (int s = 0; s < n_splits; ++s) m_star = fmaxf(m_star, __ldg(mlp + s * ml_stride).x);
-  float L = Z > 0 ? (float)Z * exp2f(-m_star) : 0.f;
-  for (int s = 0; s < n_splits; ++s) {
-    const float2 st = __ldg(mlp + s * ml_stride);
-    if (st.x != -INFINITY) L += st.y * exp2f(st.x - m_star);
+  for (int s0 = 0; s0 < n_splits; s0 += 4) {
+    float2 st[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) st[u] = (s0 + u < n_splits) ? __ldg(mlp + (size_t)(s0 + u) * ml_stride) : make_float2(-INFINITY, 0.f);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) m_star = fmaxf(m_star, st[u].x);
   }
-  const float inv_l = 1.0f / L;
+  float L = Z > 0 ? (float)Z * exp2f(-m_star) : 0.f;
   float num[kChPerCta];
 #pragma unroll
   for (int k = 0; k < kChPerCta; ++k) num[k] = 0.f;
   const size_t op_stride = (size_t)n_obj * RMNET_CV * nq_pad;
-  for (int s = 0; s < n_splits; ++s) {
-    const float mx = __ldg(mlp + s * ml_stride).x;
-    if (mx == -INFINITY) continue;  // this split saw no cells: its partial numerators are undefined
-    const float wgt = exp2f(mx - m_star);
-    const float *op = opart + s * op_stride + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
+  const float *op0 = opart + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
+  // pass 2: four splits per round, all their loads issued before use (latency-bound kernel: keep requests in flight)
+  for (int s0 = 0; s0 < n_splits; s0 += 4) {
+    float wgt[4];
 #pragma unroll
-    for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(__ldg(op + (size_t)k * nq_pad), wgt, num[k]);
+    for (int u = 0; u < 4; ++u) {
+      const float2 st = (s0 + u < n_splits) ? __ldg(mlp + (size_t)(s0 + u) * ml_stride) : make_float2(-INFINITY, 0.f);
+      wgt[u] = (st.x == -INFINITY) ? 0.f : exp2f(st.x - m_star);  // a split that saw no cells has undefined numerators
+      L += st.y * wgt[u];
+    }
+    float v[4][kChPerCta];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < kChPerCta; ++k)
+        v[u][k] = (wgt[u] != 0.f) ? __ldg(op0 + (size_t)(s0 + u) * op_stride + (size_t)k * nq_pad) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(v[u][k], wgt[u], num[k]);
   }
+  const float inv_l = 1.0f / L;
 #pragma unroll
   for (int k = 0; k < kChPerCta; ++k) out[(size_t)(c0 + k) * N] = num[k] * inv_l;
 }

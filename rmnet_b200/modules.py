@@ -86,20 +86,19 @@ class RegionalMemory:
         self.precision, self.impl = precision, impl
         self.bank = ops.MemoryBank(self.n, self.h, self.w, max_frames, device, elem_format)
 
-    def memorize(self, k4, v4, masks_padded, commit):
-        """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks_padded [1,K,Hp,Wp]: the
-        padded soft masks the reference feeds to get_att_map (:244).  Returns bboxes [1,K,4] (padded coordinates)."""
-        _, bboxes = ops.reg_att_map_forward(masks_padded, want_att=False)
-        rects = ops.cell_rects(bboxes, 0, 0, self.h, self.w, skip_channel0_every=bboxes.shape[1])
-        self.bank.memorize(k4, v4, rects[0, 1:self.n + 1].contiguous(), commit)
+    def memorize(self, k4, v4, masks, commit):
+        """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks [1,K,H,W]: the UNPADDED soft
+        masks RMNet.memorize receives (the zero padding of :212 is applied analytically).  Returns bboxes [1,K,4] in
+        padded coordinates, exactly what the reference's memorize returns (:244, :250)."""
+        bboxes, rects = ops.regional_boxes(masks, None, padded_frame=True)
+        self.bank.memorize(k4, v4, rects[0, 1:self.n + 1], commit)
         return bboxes
 
-    def read(self, k4q, v4q, prev_mask, flow):
+    def read(self, k4q, v4q, prev_mask, flow, out=None):
         """k4q [128,h,w], v4q [512,h,w]: kv_query outputs of the current frame (:315); prev_mask [1,K,H,W] and
         flow [1,2,H,W] in UNPADDED coordinates (:431).  Returns (m4 [n,1024,h,w], curr_bbox [1,K,4])."""
-        _, bbox = ops.warp_att_map_forward(prev_mask, flow, want_att=False)
-        rects = ops.cell_rects(bbox, self.lw, self.lh, self.h, self.w, skip_channel0_every=bbox.shape[1])
-        m4 = self.bank.read(k4q, v4q, rects[0, 1:self.n + 1].contiguous(), self.n, self.precision, self.impl)
+        bbox, rects = ops.regional_boxes(prev_mask, flow, padded_frame=False)
+        m4 = self.bank.read(k4q, v4q, rects[0, 1:self.n + 1], self.n, self.precision, self.impl, out=out)
         return m4, bbox
 
 

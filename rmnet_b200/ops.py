@@ -104,6 +104,32 @@ def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10
     return att, bboxes
 
 
+def regional_boxes(mask, flow=None, padded_frame=True, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64,
+                   sampler=None):
+    """One launch: bounding boxes + /16 cell rectangles from the UNPADDED soft masks [B,K,H,W].
+    flow=None, padded_frame=True  <->  pad_divide_by + get_att_map(masks) + interpolate(1/16)   (models/rmnet.py:212, :244-245)
+    flow given, padded_frame=False <->  get_att_map(prev_mask, flow) + pad + interpolate(1/16)  (:431, :307, :356)
+    -> (bboxes [B,K,4] int32, cell_rects [B,K,4] int32)"""
+    _require(mask, "mask")
+    B, K, H, W = mask.shape
+    if flow is not None:
+        _require(flow, "flow")
+        if tuple(flow.shape) != (B, 2, H, W):
+            raise RuntimeError(f"flow must be [{B},2,{H},{W}]")
+    lw, uw, lh, uh = pad_amounts(H, W)
+    dev = mask.device
+    with torch.cuda.device(dev):
+        bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
+        rects = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
+        ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
+        check(lib().rmnet_regional_boxes_forward(mask.data_ptr(), flow.data_ptr() if flow is not None else None, B, K, H, W,
+                                                 default_sampler() if sampler is None else sampler, float(prob_threshold),
+                                                 int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh,
+                                                 1 if padded_frame else 0, bboxes.data_ptr(), rects.data_ptr(), ws.data_ptr(),
+                                                 ws.numel(), _stream(dev)), "regional_boxes_forward")
+    return bboxes, rects
+
+
 def cell_rects(bboxes, pad_l, pad_t, h, w, skip_channel0_every=0):
     """Closed form of pad + F.interpolate(att_map, 1/16) for box-shaped att maps -> [..., 4] (cx0,cx1,cy0,cy1)."""
     _require(bboxes, "bboxes", torch.int32)

@@ -184,6 +184,45 @@ def test_cell_rects_equal_pad_then_downsample16():
         np.testing.assert_array_equal(got, a16)
 
 
+@pytest.mark.parametrize("size", [(480, 854), (240, 432), (100, 70), (33, 47), (96, 150)], ids=lambda s: f"{s[0]}x{s[1]}")
+def test_regional_boxes_one_launch_equals_reference_composition(size):
+    """rmnet_regional_boxes_forward on the UNPADDED masks == pad_divide_by + generator + interpolate(1/16) (memorise
+    side, models/rmnet.py:212, :244-245) and == warp + generator, then pad + interpolate(1/16) (segment side, :431, :307, :356)."""
+    H, W = size
+    K = 6
+    rng = np.random.default_rng(H * 7 + W)
+    lab = synth.rect_label_map(rng, K - 1, H, W)
+    for kind in ("onehot", "soft"):
+        mask = (synth.onehot(lab, K) if kind == "onehot" else synth.soft_masks(rng, lab, K))[None]
+        flow = synth.flow_field(rng, H, W, 3.0)[None]
+        # memorise side
+        mp, (lw, uw, lh, uh) = oracle.pad_divide_by(mask[0])
+        att_o, bb_o = oracle.reg_att_map(mp[None])
+        a16 = oracle.downsample16(att_o[0])
+        bb, rects = ops.regional_boxes(cu(mask), None, padded_frame=True)
+        np.testing.assert_array_equal(bb.cpu().numpy(), bb_o)
+        np.testing.assert_array_equal(_rects_to_grid(rects.cpu().numpy()[0], a16.shape[-2:]), a16)
+        # segment side
+        att_q, bbq_o = oracle.get_att_map(mask, flow, arith="cuda")
+        a16q = oracle.downsample16(oracle.pad_divide_by(att_q[0])[0])
+        bbq, rq = ops.regional_boxes(cu(mask), cu(flow), padded_frame=False)
+        np.testing.assert_array_equal(bbq.cpu().numpy(), bbq_o)
+        np.testing.assert_array_equal(_rects_to_grid(rq.cpu().numpy()[0], a16q.shape[-2:]), a16q)
+    # threshold <= 0: the zero padding itself passes the test, the reference's box is the whole padded frame
+    mp, _ = oracle.pad_divide_by(mask[0])
+    _, bb_o = oracle.reg_att_map(mp[None], prob_threshold=0.0)
+    bb, _ = ops.regional_boxes(cu(mask), None, padded_frame=True, prob_threshold=0.0)
+    np.testing.assert_array_equal(bb.cpu().numpy(), bb_o)
+
+
+def _rects_to_grid(rects, hw):
+    g = np.zeros((rects.shape[0],) + tuple(hw), np.float32)
+    for i, (cx0, cx1, cy0, cy1) in enumerate(rects):
+        if cx0 <= cx1 and cy0 <= cy1:
+            g[i, cy0:cy1 + 1, cx0:cx1 + 1] = 1
+    return g
+
+
 def test_flow_affine_bit_exact(golden_dir):
     g = np.load(os.path.join(golden_dir, "flow_affine.npz"))
     for i in range(int(g["n_cases"])):  # golden vectors produced by the reference extension
@@ -267,7 +306,7 @@ def _regional_setup(seed, n, T, H, W):
     mk, mv, qk, qv = synth.memory_read_inputs(seed + 1, n, T, h, w, 0.5)
     masks = []
     for t in range(T):
-        lab = synth.rect_label_map(rng, n, Hp, Wp)
+        lab = synth.rect_label_map(rng, n, H, W)     # UNPADDED, as RMNet.memorize receives them (models/rmnet.py:207-212)
         masks.append(synth.soft_masks(rng, lab, K) if t % 2 else synth.onehot(lab, K))
     prev = synth.onehot(synth.rect_label_map(rng, n, H, W), K)
     flow = synth.flow_field(rng, H, W, 3.0)
@@ -278,7 +317,8 @@ def _regional_setup(seed, n, T, H, W):
 def _regional_oracle(s, T_used):
     """The reference's composition (models/rmnet.py:244-248 per memory frame, :431/:307/:355-361 for the query)."""
     n = s["n"]
-    att_m = np.stack([oracle.reg_att_map(s["masks"][t][None])[0][0, 1:n + 1] for t in range(T_used)], 1)  # [n,T,Hp,Wp]
+    att_m = np.stack([oracle.reg_att_map(oracle.pad_divide_by(s["masks"][t])[0][None])[0][0, 1:n + 1]
+                      for t in range(T_used)], 1)                                                    # [n,T,Hp,Wp] (:212, :244)
     att_q, bb_q = oracle.get_att_map(s["prev"][None], s["flow"][None], arith="cuda")
     att_qp, _ = oracle.pad_divide_by(att_q[0, 1:n + 1])
     ref = oracle.regional_memory_read(s["mk"][:, :, :T_used], s["mv"][:, :, :T_used], att_m, s["qk"], s["qv"], att_qp,
@@ -303,7 +343,7 @@ def test_regional_path_vs_oracle_with_temp_and_commit(impl_name, impl, cfg):
         k4 = cu(s["mk"][:, :, t])
         v4 = cu(s["mv"][:, :, t])
         bb = rm.memorize(k4.contiguous(), v4.contiguous(), cu(s["masks"][t][None]), commit)
-        _, bb_o = oracle.reg_att_map(s["masks"][t][None])
+        _, bb_o = oracle.reg_att_map(oracle.pad_divide_by(s["masks"][t])[0][None])
         np.testing.assert_array_equal(bb.cpu().numpy(), bb_o)
         m4, cur_bb = rm.read(cu(s["qk"]), cu(s["qv"]), cu(s["prev"][None]), cu(s["flow"][None]))
         sub = dict(s)

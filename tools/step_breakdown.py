@@ -13,24 +13,21 @@ for wlname in ("c2", "c3"):
     h, w, lw, Wp = pool["h"], pool["w"], pool["lw"], pool["Wp"]
     rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=dev)
     fr = pool["frames"]
-    D = lambda f: {k: torch.from_numpy(v).to(dev) for k, v in f.items()} | {"maskp": torch.from_numpy(bench.pad_mask(f["mask"], lw, Wp)).to(dev)}
+    D = lambda f: {k: torch.from_numpy(v).to(dev) for k, v in f.items()}
     for t in range(T - 1):
-        d = D(fr[t]); rm.memorize(d["k4"], d["v4"], d["maskp"][None].contiguous(), commit=True)
+        d = D(fr[t]); rm.memorize(d["k4"], d["v4"], d["mask"][None], commit=True)
     d = D(fr[T - 1])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    _, bb = ops.reg_att_map_forward(d["maskp"][None], want_att=False)
-    rects = ops.cell_rects(bb, 0, 0, h, w, skip_channel0_every=11)[0, 1:n + 1].contiguous()
-    _, bbq = ops.warp_att_map_forward(d["mask"][None], d["flow"][None], want_att=False)
-    rq = ops.cell_rects(bbq, lw, 0, h, w, skip_channel0_every=11)[0, 1:n + 1].contiguous()
+    rects = ops.regional_boxes(d["mask"][None], None, True)[1][0, 1:n + 1].contiguous()
+    rq = ops.regional_boxes(d["mask"][None], d["flow"][None], False)[1][0, 1:n + 1].contiguous()
     out = torch.empty((n, 1024, h, w), device=dev)
     opsd = {
-        "generator(bbox only)": lambda: ops.reg_att_map_forward(d["maskp"][None], want_att=False),
-        "cell_rects": lambda: ops.cell_rects(bb, 0, 0, h, w, skip_channel0_every=11),
+        "boxes+rects (memorise side)": lambda: ops.regional_boxes(d["mask"][None], None, True),
         "bank.memorize(temp)": lambda: rm.bank.memorize(d["k4"], d["v4"], rects, False),
-        "warp+bbox fused": lambda: ops.warp_att_map_forward(d["mask"][None], d["flow"][None], want_att=False),
+        "warp+boxes+rects (segment)": lambda: ops.regional_boxes(d["mask"][None], d["flow"][None], False),
         "read: attention kernel": lambda: rm.bank.read(d["qk"], d["qv"], rq, n, stages=1, out=out),
         "read: merge kernel": lambda: rm.bank.read(d["qk"], d["qv"], rq, n, stages=2, out=out),
-        "whole step": lambda: (rm.memorize(d["k4"], d["v4"], d["maskp"][None], commit=False), rm.read(d["qk"], d["qv"], d["mask"][None], d["flow"][None])),
+        "whole step": lambda: (rm.memorize(d["k4"], d["v4"], d["mask"][None], commit=False), rm.read(d["qk"], d["qv"], d["mask"][None], d["flow"][None])),
     }
     print("==", wlname, "cells/object", (rm.bank.stats()[:n, 0] + rm.bank.stats()[:n, 1]).tolist())
     for name, fn in opsd.items():
