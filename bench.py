@@ -218,8 +218,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_dev(d):
-        rm.memorize(d["k4"], d["v4"], d["mask"][None], commit=False)
-        m4, _ = rm.read(d["qk"], d["qv"], d["mask"][None], d["flow"][None])
+        m4, _, _ = rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
         return m4
 
     h2d = sum(v.numel() * 4 for v in hframes[0].values())
@@ -285,8 +284,8 @@ def run_gpu(args, wl, rank, world, local_rank):
                 main.wait_event(ev_in[b])
                 if i >= 3:
                     main.wait_event(ev_out[b])               # the D2H of step i-3 released this output buffer
-                rm.memorize(dbuf[b]["k4"], dbuf[b]["v4"], dbuf[b]["mask"][None], commit=False)
-                rm.read(dbuf[b]["qk"], dbuf[b]["qv"], dbuf[b]["mask"][None], dbuf[b]["flow"][None], out=obuf[b])
+                rm.step(dbuf[b]["k4"], dbuf[b]["v4"], dbuf[b]["mask"][None], dbuf[b]["flow"][None], dbuf[b]["qk"], dbuf[b]["qv"],
+                        commit=False, out=obuf[b])
                 ev_free[b].record(main)
                 ev_done[b].record(main)
                 with torch.cuda.stream(s_out):
@@ -355,10 +354,10 @@ def run_gpu(args, wl, rank, world, local_rank):
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 hi/lo split x3, fp32 accumulate" if passes == 3 else "bf16 x1, fp32 accumulate", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path "
-                               "(generator + pack-at-memorise + fused warp/bbox + regional read of all objects; 6 kernel launches)",
+                               "(generator + pack-at-memorise + fused warp/bbox + regional read of all objects; 4 kernels + 1 memset per step: RegionalMemory.step)",
                    "clips_per_gpu": 1, "parallelism": f"clip-parallel x{world} (no data-path collective)", "precision": args.precision,
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed", "pool_frames": POOL,
-                   "e2e_mode": "pinned host inputs -> H2D -> 6 kernels -> D2H of mem_val every step; copies double-buffered on side streams"},
+                   "e2e_mode": "pinned host inputs -> H2D -> RegionalMemory.step -> D2H of mem_val every step; copies double-buffered on side streams"},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches, "roofline": roof, "clocks": clk, "result_checksum": checksum,
     }

@@ -120,6 +120,15 @@ RMNET_API int rmnet_regional_boxes_forward(const float *mask, const float *flow,
                                            int bbox_in_padded_frame, int *bboxes, int *cell_rects,
                                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* Both sides of one frame in ONE pass over prev_mask (the memorise side and the segment side read the same
+ * est_masks[t-1], models/rmnet.py:412-414 and :431): mem_* = box of the zero-padded mask in padded coordinates and
+ * its cell rectangles; cur_* = box of the flow-warped mask in raw coordinates and its cell rectangles. */
+RMNET_API int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
+                                          int sampler, float prob_threshold, int n_pts_threshold,
+                                          int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t, int pad_b,
+                                          int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
+                                          void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Low-resolution cell rectangles: the closed form of
  *   F.interpolate(pad(att_map), scale_factor=1/16)             (models/rmnet.py:245, :307+:356)

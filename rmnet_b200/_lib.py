@@ -36,6 +36,9 @@ PROTOTYPES = {
                                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_regional_boxes_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                              c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rmnet_frame_regions_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
+                                            c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_void_p]),
     "rmnet_cell_rects_from_bboxes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rmnet_bank_bytes": (c_size_t, [c_int, c_int]),
     "rmnet_bank_reset": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),

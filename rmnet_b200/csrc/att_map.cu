@@ -102,7 +102,7 @@ bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr,
   const int b = blockIdx.z, i = blockIdx.y + 1;
   const long long n_pixels = (long long)H * W;
   const float *plane = mask + ((long long)b * K + i) * n_pixels;
-  int *ws_ch = ws + ((long long)b * (K + 1) + i) * kWsIntsPerChannel;
+  int *ws_ch = ws + ((long long)b * 2 * (K + 1) + i) * kWsIntsPerChannel;
   const long long begin = (long long)blockIdx.x * elems_per_cta;
   const long long end = min(begin + (long long)elems_per_cta, n_pixels);
 
@@ -122,6 +122,8 @@ bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr,
       for (int u = 0; u < 4; ++u) {
         long long j = j0 + (long long)u * kThreads * 4;
         if (j >= end) continue;
+        // fast path: most 16-byte groups hold no foreground pixel at all (4 compares, no index arithmetic)
+        if (!((v[u].x >= thr) | (v[u].y >= thr) | (v[u].z >= thr) | (v[u].w >= thr))) continue;
         int y = (int)(j / W), x = (int)(j - (long long)y * W);
         const float e[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
@@ -271,63 +273,106 @@ warp_kernel(const float *__restrict__ img0, const float *__restrict__ flow, int 
   }
 }
 
-// ---- fused warp + threshold + bbox: grid (pixel tiles, B) ----------------------------------------
-constexpr int kPixPerThread = 2;
-template <int ORDER>
+// ---- fused warp + threshold + bbox: grid (pixel tiles, B), one pixel per thread ------------------------
+// One pass over prev_mask produces the box of the flow-warped mask (segment side, models/rmnet.py:431) and, when
+// DIRECT, also the box of the mask itself (memorise side, :244) -- both read the same est_masks[t-1].
+// Channels are processed five at a time with all their loads (4 taps + 1 direct) issued before use: the gathers
+// follow the flow and are the latency bottleneck.  A warp covers 32 consecutive pixels; when they lie in one row
+// the per-channel box of the warp comes straight from the ballot (popc / ffs / clz), else from REDUX.
+constexpr int kChunkCh = 5;
+
+__device__ __forceinline__ void warp_box_to_smem(int *s_acc, unsigned ballot, bool one_row, int x_lane0, int y_lane0,
+                                                 bool hit, int x, int y, int lane) {
+  if (ballot == 0u) return;
+  int cnt, xmin, xmax, ymin, ymax;
+  if (one_row) {
+    cnt = __popc(ballot);
+    xmin = x_lane0 + (__ffs(ballot) - 1);
+    xmax = x_lane0 + (31 - __clz(ballot));
+    ymin = ymax = y_lane0;
+  } else {
+    cnt = __popc(ballot);
+    xmin = __reduce_min_sync(0xffffffffu, hit ? x : 32767);
+    xmax = __reduce_max_sync(0xffffffffu, hit ? x : 0);
+    ymin = __reduce_min_sync(0xffffffffu, hit ? y : 32767);
+    ymax = __reduce_max_sync(0xffffffffu, hit ? y : 0);
+  }
+  if (lane == 0) {
+    atomicAdd(s_acc + 0, cnt);
+    atomicMax(s_acc + 1, 32767 - xmin);
+    atomicMax(s_acc + 2, xmax);
+    atomicMax(s_acc + 3, 32767 - ymin);
+    atomicMax(s_acc + 4, ymax);
+  }
+}
+
+template <int ORDER, bool DIRECT>
 __global__ void __launch_bounds__(kThreads)
-warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
-                 float inv_w, float inv_h, float thr, BoxFinalize fin, int *__restrict__ bboxes,
-                 int *__restrict__ ws) {
-  extern __shared__ int s_acc[];  // [K][5] CTA accumulators (zero identity, mins inverted)
+frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
+                   float inv_w, float inv_h, float thr, BoxFinalize fin_warp, BoxFinalize fin_direct,
+                   int *__restrict__ bboxes_warp, int *__restrict__ bboxes_direct, int *__restrict__ ws) {
+  extern __shared__ int s_acc[];  // [2][K][5] CTA accumulators (zero identity, mins inverted): warped, direct
   __shared__ bool s_last;
   const int b = blockIdx.y;
   const long long n_pixels = (long long)H * W;
   const float *fl = flow + (long long)b * 2 * n_pixels;
-  for (int k = threadIdx.x; k < K * 5; k += kThreads) s_acc[k] = 0;
+  for (int k = threadIdx.x; k < 2 * K * 5; k += kThreads) s_acc[k] = 0;
   __syncthreads();
 
-  Tap taps[kPixPerThread];
-  int px[kPixPerThread], py[kPixPerThread];
-  bool live[kPixPerThread];
-  const long long base = (long long)blockIdx.x * kThreads * kPixPerThread + threadIdx.x;
-#pragma unroll
-  for (int p = 0; p < kPixPerThread; ++p) {
-    const long long j = base + (long long)p * kThreads;
-    live[p] = j < n_pixels;
-    const long long jj = live[p] ? j : 0;
-    py[p] = (int)(jj / W);
-    px[p] = (int)(jj - (long long)py[p] * W);
-    taps[p] = make_tap<ORDER>(px[p], py[p], __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
-  }
+  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
+  const bool live = j < n_pixels;
+  const long long jj = live ? j : n_pixels - 1;
+  const int y = (int)(jj / W), x = (int)(jj - (long long)y * W);
   const int lane = threadIdx.x & 31;
-  for (int i = 1; i < K; ++i) {
-    const float *plane = prev_mask + ((long long)b * K + i) * n_pixels;
-    BoxAcc acc;
-    acc.init();
+  const int x_lane0 = __shfl_sync(0xffffffffu, x, 0), y_lane0 = __shfl_sync(0xffffffffu, y, 0);
+  const bool one_row = __shfl_sync(0xffffffffu, y, 31) == y_lane0 && __all_sync(0xffffffffu, live);
+  const Tap t = make_tap<ORDER>(x, y, __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
+  const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+  const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+  const bool p_nw = xin0 && yin0, p_ne = xin1 && yin0, p_sw = xin0 && yin1, p_se = xin1 && yin1;
+  const long long o_nw = (long long)t.y0 * W + t.x0;
+
+  for (int i0 = 1; i0 < K; i0 += kChunkCh) {
+    float v_nw[kChunkCh], v_ne[kChunkCh], v_sw[kChunkCh], v_se[kChunkCh], v_d[kChunkCh];
 #pragma unroll
-    for (int p = 0; p < kPixPerThread; ++p) {
-      if (live[p] && sample_tap<ORDER>(plane, taps[p], H, W) >= thr) acc.hit(px[p], py[p]);
+    for (int u = 0; u < kChunkCh; ++u) {
+      const int i = min(i0 + u, K - 1);
+      const float *plane = prev_mask + ((long long)b * K + i) * n_pixels;
+      v_nw[u] = p_nw ? __ldg(plane + o_nw) : 0.f;
+      v_ne[u] = p_ne ? __ldg(plane + o_nw + 1) : 0.f;
+      v_sw[u] = p_sw ? __ldg(plane + o_nw + W) : 0.f;
+      v_se[u] = p_se ? __ldg(plane + o_nw + W + 1) : 0.f;
+      if (DIRECT) v_d[u] = __ldg(plane + jj);
     }
-    if (!__any_sync(0xffffffffu, acc.cnt > 0)) continue;  // background warp: nothing to reduce for this channel
-    acc.warp_reduce();
-    if (lane == 0) {
-      atomicAdd(&s_acc[i * 5 + 0], acc.cnt);
-      atomicMax(&s_acc[i * 5 + 1], 32767 - acc.xmin);
-      atomicMax(&s_acc[i * 5 + 2], acc.xmax);
-      atomicMax(&s_acc[i * 5 + 3], 32767 - acc.ymin);
-      atomicMax(&s_acc[i * 5 + 4], acc.ymax);
+#pragma unroll
+    for (int u = 0; u < kChunkCh; ++u) {
+      const int i = i0 + u;
+      if (i >= K) break;  // warp-uniform
+      // same FMA chain as sample_tap (an out-of-bounds tap contributes fma(0, w, acc) = acc exactly)
+      float acc;
+      if (ORDER == 1) acc = __fmaf_rn(v_ne[u], t.ne, __fmul_rn(v_nw[u], t.nw));
+      else acc = __fmaf_rn(v_nw[u], t.nw, __fmul_rn(v_ne[u], t.ne));
+      acc = __fmaf_rn(v_se[u], t.se, __fmaf_rn(v_sw[u], t.sw, acc));
+      const bool hit_w = live && (__fmul_rn(acc, t.valid) >= thr);
+      warp_box_to_smem(s_acc + i * 5, __ballot_sync(0xffffffffu, hit_w), one_row, x_lane0, y_lane0, hit_w, x, y, lane);
+      if (DIRECT) {
+        const bool hit_d = live && (v_d[u] >= thr);
+        warp_box_to_smem(s_acc + (K + i) * 5, __ballot_sync(0xffffffffu, hit_d), one_row, x_lane0, y_lane0, hit_d, x, y, lane);
+      }
     }
   }
   __syncthreads();
-  int *ws_b = ws + (long long)b * (K + 1) * kWsIntsPerChannel;
-  for (int i = 1 + threadIdx.x; i < K; i += kThreads) {
-    if (s_acc[i * 5] > 0) {
-      int *w = ws_b + i * kWsIntsPerChannel;
-      atomicAdd(w + 0, s_acc[i * 5 + 0]);
-      atomicMax(w + 1, s_acc[i * 5 + 1]);
-      atomicMax(w + 2, s_acc[i * 5 + 2]);
-      atomicMax(w + 3, s_acc[i * 5 + 3]);
-      atomicMax(w + 4, s_acc[i * 5 + 4]);
+  // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it
+  int *ws_b = ws + (long long)b * 2 * (K + 1) * kWsIntsPerChannel;
+  for (int e = threadIdx.x; e < (DIRECT ? 2 : 1) * K; e += kThreads) {
+    const int set = e / K, i = e - set * K;
+    if (i >= 1 && s_acc[e * 5] > 0) {
+      int *w = ws_b + (set * (K + 1) + i) * kWsIntsPerChannel;
+      atomicAdd(w + 0, s_acc[e * 5 + 0]);
+      atomicMax(w + 1, s_acc[e * 5 + 1]);
+      atomicMax(w + 2, s_acc[e * 5 + 2]);
+      atomicMax(w + 3, s_acc[e * 5 + 3]);
+      atomicMax(w + 4, s_acc[e * 5 + 4]);
     }
   }
   __threadfence();
@@ -339,9 +384,12 @@ warp_bbox_kernel(const float *__restrict__ prev_mask, const float *__restrict__ 
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int i = threadIdx.x; i < K; i += kThreads) {
-      if (i == 0) finalize_channel0(bboxes, (long long)b * K, fin);
-      else finalize_channel(ws_b + i * kWsIntsPerChannel, bboxes, (long long)b * K + i, fin);
+    for (int e = threadIdx.x; e < (DIRECT ? 2 : 1) * K; e += kThreads) {
+      const int set = e / K, i = e - set * K;
+      int *bb = set ? bboxes_direct : bboxes_warp;
+      const BoxFinalize &f = set ? fin_direct : fin_warp;
+      if (i == 0) finalize_channel0(bb, (long long)b * K, f);
+      else finalize_channel(ws_b + (set * (K + 1) + i) * kWsIntsPerChannel, bb, (long long)b * K + i, f);
     }
     if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);
   }
@@ -397,7 +445,24 @@ using namespace rmnet;
 extern "C" {
 
 size_t rmnet_reg_att_map_workspace_bytes(int B, int K) {
-  return (size_t)B * (K + 1) * kWsIntsPerChannel * sizeof(int);
+  return (size_t)B * 2 * (K + 1) * kWsIntsPerChannel * sizeof(int);  // two accumulator sets (warped, direct)
+}
+
+static void make_finalize(BoxFinalize &fin, bool padded, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b, float thr,
+                          int n_pts, int loose, int *rects) {
+  fin.Hf = padded ? H + pad_t + pad_b : H;
+  fin.Wf = padded ? W + pad_l + pad_r : W;
+  fin.off_x = padded ? pad_l : 0;
+  fin.off_y = padded ? pad_t : 0;
+  fin.n_pts_threshold = n_pts;
+  fin.loose = loose;
+  // zero padding passes a threshold <= 0: every padded pixel is a point, the loosened box is the whole frame
+  fin.force_full = (padded && thr <= 0.0f && (pad_l | pad_r | pad_t | pad_b) && (long long)fin.Hf * fin.Wf >= n_pts) ? 1 : 0;
+  fin.rects = rects;
+  fin.rect_pad_l = padded ? 0 : pad_l;
+  fin.rect_pad_t = padded ? 0 : pad_t;
+  fin.cell_h = (H + pad_t + pad_b) / 16;
+  fin.cell_w = (W + pad_l + pad_r) / 16;
 }
 
 static int launch_scan(const float *mask, int B, int K, int H, int W, float thr, const BoxFinalize &fin, int *bboxes,
@@ -418,20 +483,26 @@ static int launch_scan(const float *mask, int B, int K, int H, int W, float thr,
   return RMNET_OK;
 }
 
-static int launch_warp_scan(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler, float thr,
-                            const BoxFinalize &fin, int *bboxes, void *workspace, cudaStream_t st) {
+static int launch_frame_boxes(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler, float thr,
+                              const BoxFinalize &fin_warp, int *bboxes_warp, const BoxFinalize *fin_direct, int *bboxes_direct,
+                              void *workspace, cudaStream_t st) {
   const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
   const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
-  const int per_cta = kThreads * kPixPerThread;
-  dim3 grid((unsigned)(((long long)H * W + per_cta - 1) / per_cta), B);
-  if (sampler == RMNET_SAMPLER_CUDNN)
-    warp_bbox_kernel<0><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin, bboxes,
-                                                                     (int *)workspace);
-  else
-    warp_bbox_kernel<1><<<grid, kThreads, K * 5 * sizeof(int), st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin, bboxes,
-                                                                     (int *)workspace);
+  dim3 grid((unsigned)(((long long)H * W + kThreads - 1) / kThreads), B);
+  const size_t smem = 2 * K * 5 * sizeof(int);
+  const BoxFinalize fd = fin_direct ? *fin_direct : fin_warp;
+#define RMNET_LAUNCH_FB(O, D)                                                                                              \
+  frame_boxes_kernel<O, D><<<grid, kThreads, smem, st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin_warp, fd, bboxes_warp, \
+                                                         bboxes_direct, (int *)workspace)
+  if (sampler == RMNET_SAMPLER_CUDNN) { if (fin_direct) RMNET_LAUNCH_FB(0, true); else RMNET_LAUNCH_FB(0, false); }
+  else { if (fin_direct) RMNET_LAUNCH_FB(1, true); else RMNET_LAUNCH_FB(1, false); }
+#undef RMNET_LAUNCH_FB
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
+}
+static int launch_warp_scan(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler, float thr,
+                            const BoxFinalize &fin, int *bboxes, void *workspace, cudaStream_t st) {
+  return launch_frame_boxes(prev_mask, flow, B, K, H, W, sampler, thr, fin, bboxes, nullptr, nullptr, workspace, st);
 }
 
 int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,
@@ -460,21 +531,8 @@ int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, in
   RMNET_CHECK_ARG(K <= 1024, "K too large");
   cudaStream_t st = (cudaStream_t)stream;
   BoxFinalize fin;
-  const bool padded = bbox_in_padded_frame != 0;
-  fin.Hf = padded ? H + pad_t + pad_b : H;
-  fin.Wf = padded ? W + pad_l + pad_r : W;
-  fin.off_x = padded ? pad_l : 0;
-  fin.off_y = padded ? pad_t : 0;
-  fin.n_pts_threshold = n_pts_threshold;
-  fin.loose = n_bbox_loose_pixels;
-  // zero padding passes a threshold <= 0: every padded pixel is a point, the loosened box is the whole frame
-  fin.force_full = (padded && prob_threshold <= 0.0f && (pad_l | pad_r | pad_t | pad_b) &&
-                    (long long)fin.Hf * fin.Wf >= n_pts_threshold) ? 1 : 0;
-  fin.rects = cell_rects;
-  fin.rect_pad_l = padded ? 0 : pad_l;
-  fin.rect_pad_t = padded ? 0 : pad_t;
-  fin.cell_h = (H + pad_t + pad_b) / 16;
-  fin.cell_w = (W + pad_l + pad_r) / 16;
+  make_finalize(fin, bbox_in_padded_frame != 0, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold,
+                n_bbox_loose_pixels, cell_rects);
   if (flow) return launch_warp_scan(mask, flow, B, K, H, W, sampler, prob_threshold, fin, bboxes, workspace, st);
   return launch_scan(mask, B, K, H, W, prob_threshold, fin, bboxes, workspace, st);
 }
@@ -493,6 +551,26 @@ int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H
     warp_kernel<1><<<grid, kThreads, 0, (cudaStream_t)stream>>>(img0, flow, C, H, W, inv_w, inv_h, img1, valid);
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
+}
+
+int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
+                                float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
+                                int pad_t, int pad_b, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
+                                void *workspace, size_t workspace_bytes, void *stream) {
+  int rc = check_common(prev_mask, B, K, H, W, mem_bboxes, workspace, workspace_bytes);
+  if (rc) return rc;
+  RMNET_CHECK_ARG(flow && cur_bboxes && mem_rects && cur_rects, "null pointer argument");
+  RMNET_CHECK_ARG(pad_l >= 0 && pad_r >= 0 && pad_t >= 0 && pad_b >= 0, "negative padding");
+  RMNET_CHECK_ARG((H + pad_t + pad_b) % 16 == 0 && (W + pad_l + pad_r) % 16 == 0, "padded frame must be a multiple of 16");
+  RMNET_CHECK_ARG(H + pad_t + pad_b <= 32767 && W + pad_l + pad_r <= 32767, "padded frame too large");
+  RMNET_CHECK_ARG(((uintptr_t)cur_bboxes | (uintptr_t)mem_rects | (uintptr_t)cur_rects) % 16 == 0, "outputs must be 16-byte aligned");
+  RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
+  RMNET_CHECK_ARG(K <= 512, "K too large");
+  BoxFinalize fw, fd;
+  make_finalize(fw, false, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, cur_rects);
+  make_finalize(fd, true, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, mem_rects);
+  return launch_frame_boxes(prev_mask, flow, B, K, H, W, sampler, prob_threshold, fw, cur_bboxes, &fd, mem_bboxes, workspace,
+                            (cudaStream_t)stream);
 }
 
 int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,

@@ -323,17 +323,22 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       const bool live = n < nq;
       const float *qp = q_key + (long long)o * q_obj_stride + (live ? rect_pos(qrect, n, w) : 0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < RMNET_CK; c0 += 32) {
-        uint32_t hi[16], lo[16];
+      for (int c0 = 0; c0 < RMNET_CK; c0 += 64) {  // 64 strided loads in flight per thread per pass
+        float xq[64];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x0 = live ? __ldg(qp + (long long)(c0 + 2 * j) * N) : 0.f;
-          const float x1 = live ? __ldg(qp + (long long)(c0 + 2 * j + 1) * N) : 0.f;
+        for (int j = 0; j < 64; ++j) xq[j] = live ? __ldg(qp + (long long)(c0 + j) * N) : 0.f;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
           lo[j] = 0;
-          split_pack2<FMT, USE_LO>(x0, x1, hi[j], lo[j]);
+          split_pack2<FMT, USE_LO>(xq[2 * j], xq[2 * j + 1], hi[j], lo[j]);
         }
         TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
-        if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
+        TMEM_ST16(t_base + TM_Q_HI + c0 / 2 + 16, hi, 16);
+        if (USE_LO) {
+          TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
+          TMEM_ST16(t_base + TM_Q_LO + c0 / 2 + 16, lo, 16);
+        }
       }
       tc_wait_st();
       tc_fence_before();

@@ -53,40 +53,45 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   const int half = c0 / (RMNET_CV / 2);
   const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((size_t)o * 2 + half) * nq_pad + n;
   const size_t ml_stride = (size_t)n_obj * 2 * nq_pad;  // between consecutive splits
-  // pass 1: statistics of every split (8 B each, independent loads), reference max, denominator
-  float m_star = Z > 0 ? 0.f : -INFINITY;
-  for (int s0 = 0; s0 < n_splits; s0 += 4) {
-    float2 st[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) st[u] = (s0 + u < n_splits) ? __ldg(mlp + (size_t)(s0 + u) * ml_stride) : make_float2(-INFINITY, 0.f);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) m_star = fmaxf(m_star, st[u].x);
-  }
-  float L = Z > 0 ? (float)Z * exp2f(-m_star) : 0.f;
+  // Single pass over the splits, four per round with every load of the round issued before use (the kernel is
+  // latency bound).  Online max: the running numerators / denominator are rescaled when a round raises it.
+  // Loads of the partial numerators are unconditional -- a split that saw no cells (max = -inf) left them
+  // unwritten, so its values are discarded by selection, never multiplied.
+  float m_run = Z > 0 ? 0.f : -INFINITY;
+  float L = Z > 0 ? (float)Z : 0.f;  // Z * 2^(0 - m_run) with m_run = 0
   float num[kChPerCta];
 #pragma unroll
   for (int k = 0; k < kChPerCta; ++k) num[k] = 0.f;
   const size_t op_stride = (size_t)n_obj * RMNET_CV * nq_pad;
   const float *op0 = opart + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
-  // pass 2: four splits per round, all their loads issued before use (latency-bound kernel: keep requests in flight)
   for (int s0 = 0; s0 < n_splits; s0 += 4) {
-    float wgt[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const float2 st = (s0 + u < n_splits) ? __ldg(mlp + (size_t)(s0 + u) * ml_stride) : make_float2(-INFINITY, 0.f);
-      wgt[u] = (st.x == -INFINITY) ? 0.f : exp2f(st.x - m_star);  // a split that saw no cells has undefined numerators
-      L += st.y * wgt[u];
-    }
+    float2 st[4];
     float v[4][kChPerCta];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 4; ++u) {
+      const int s = min(s0 + u, n_splits - 1);
+      st[u] = __ldg(mlp + (size_t)s * ml_stride);
+      if (s0 + u >= n_splits) st[u] = make_float2(-INFINITY, 0.f);
 #pragma unroll
-      for (int k = 0; k < kChPerCta; ++k)
-        v[u][k] = (wgt[u] != 0.f) ? __ldg(op0 + (size_t)(s0 + u) * op_stride + (size_t)k * nq_pad) : 0.f;
+      for (int k = 0; k < kChPerCta; ++k) v[u][k] = __ldg(op0 + (size_t)s * op_stride + (size_t)k * nq_pad);
+    }
+    float m_new = m_run;
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 4; ++u) m_new = fmaxf(m_new, st[u].x);
+    if (m_new == -INFINITY) continue;  // nothing seen so far
+    const float f = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
+    L *= f;
 #pragma unroll
-      for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(v[u][k], wgt[u], num[k]);
+    for (int k = 0; k < kChPerCta; ++k) num[k] *= f;
+    m_run = m_new;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (st[u].x == -INFINITY) continue;
+      const float wgt = exp2f(st[u].x - m_run);
+      L = fmaf(st[u].y, wgt, L);
+#pragma unroll
+      for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(v[u][k], wgt, num[k]);
+    }
   }
   const float inv_l = 1.0f / L;
 #pragma unroll

@@ -102,6 +102,16 @@ class RegionalMemory:
         return m4, bbox
 
 
+    def step(self, k4, v4, prev_mask, flow, k4q, v4q, commit, out=None):
+        """One frame of the reference's loop body (models/rmnet.py:414-432 minus the convs) in 4 launches:
+        regions of both sides from ONE pass over prev_mask, pack k4/v4 (memorise), read for the current frame.
+        Returns (m4 [n,1024,h,w], prev_bbox [1,K,4] padded coords, curr_bbox [1,K,4] raw coords)."""
+        mem_bb, mem_rects, cur_bb, cur_rects = ops.frame_regions(prev_mask, flow)
+        self.bank.memorize(k4, v4, mem_rects[0, 1:self.n + 1], commit)
+        m4 = self.bank.read(k4q, v4q, cur_rects[0, 1:self.n + 1], self.n, self.precision, self.impl, out=out)
+        return m4, mem_bb, cur_bb
+
+
 def install(models_rmnet_module):
     """Rebind the reference's names so that an unmodified core/inference.py builds an RMNet that runs on this
     library (RMNet.__init__ looks the classes up at construction time, models/rmnet.py:187-189)."""

@@ -130,6 +130,27 @@ def regional_boxes(mask, flow=None, padded_frame=True, prob_threshold=0.5, n_pts
     return bboxes, rects
 
 
+def frame_regions(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64, sampler=None):
+    """Both region descriptors of a frame in one pass over prev_mask [B,K,H,W] (unpadded) and flow [B,2,H,W]:
+    -> (mem_bboxes, mem_rects, cur_bboxes, cur_rects), each [B,K,4] int32  (see regional_boxes for the two halves)."""
+    _require(prev_mask, "prev_mask")
+    _require(flow, "flow")
+    B, K, H, W = prev_mask.shape
+    if tuple(flow.shape) != (B, 2, H, W):
+        raise RuntimeError(f"flow must be [{B},2,{H},{W}]")
+    lw, uw, lh, uh = pad_amounts(H, W)
+    dev = prev_mask.device
+    with torch.cuda.device(dev):
+        out = torch.empty((4, B, K, 4), dtype=torch.int32, device=dev)
+        ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
+        check(lib().rmnet_frame_regions_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
+                                                default_sampler() if sampler is None else sampler, float(prob_threshold),
+                                                int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh,
+                                                out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
+                                                ws.data_ptr(), ws.numel(), _stream(dev)), "frame_regions_forward")
+    return out[0], out[1], out[2], out[3]
+
+
 def cell_rects(bboxes, pad_l, pad_t, h, w, skip_channel0_every=0):
     """Closed form of pad + F.interpolate(att_map, 1/16) for box-shaped att maps -> [..., 4] (cx0,cx1,cy0,cy1)."""
     _require(bboxes, "bboxes", torch.int32)

@@ -208,6 +208,10 @@ def test_regional_boxes_one_launch_equals_reference_composition(size):
         bbq, rq = ops.regional_boxes(cu(mask), cu(flow), padded_frame=False)
         np.testing.assert_array_equal(bbq.cpu().numpy(), bbq_o)
         np.testing.assert_array_equal(_rects_to_grid(rq.cpu().numpy()[0], a16q.shape[-2:]), a16q)
+        # both sides in one pass over the mask
+        mb, mr, cb, cr = ops.frame_regions(cu(mask), cu(flow))
+        for got, want in ((mb, bb), (mr, rects), (cb, bbq), (cr, rq)):
+            np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy())
     # threshold <= 0: the zero padding itself passes the test, the reference's box is the whole padded frame
     mp, _ = oracle.pad_divide_by(mask[0])
     _, bb_o = oracle.reg_att_map(mp[None], prob_threshold=0.0)
@@ -360,6 +364,25 @@ def test_regional_path_vs_oracle_with_temp_and_commit(impl_name, impl, cfg):
     st = rm.bank.stats()
     assert (st[:n, 4] + st[:n, 5] == len(committed) + (0 if (T - 1) % 2 == 0 else 1)).all()
     assert (st[:n, 6] == 0).all()   # no overflow
+
+
+def test_step_equals_memorize_then_read():
+    """RegionalMemory.step (one pass over prev_mask for both sides) == memorize() + read() on the same inputs; the
+    same est_masks[t-1] feeds both sides in the reference loop (models/rmnet.py:412-414, :431)."""
+    n, T, H, W = 3, 3, 240, 432
+    s = _regional_setup(81, n, T, H, W)
+    a = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV)
+    b = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV)
+    for t in range(T):
+        k4, v4 = cu(s["mk"][:, :, t]), cu(s["mv"][:, :, t])
+        mask, flow = cu(s["masks"][t][None]), cu(s["flow"][None])
+        bb1 = a.memorize(k4, v4, mask, commit=(t < T - 1))
+        m1, cb1 = a.read(cu(s["qk"]), cu(s["qv"]), mask, flow)
+        m2, bb2, cb2 = b.step(k4, v4, mask, flow, cu(s["qk"]), cu(s["qv"]), commit=(t < T - 1))
+        np.testing.assert_array_equal(bb1.cpu().numpy(), bb2.cpu().numpy())
+        np.testing.assert_array_equal(cb1.cpu().numpy(), cb2.cpu().numpy())
+        assert (m1 - m2).abs().max().item() <= 1e-6   # identical kernels; only the vsum atomics may reorder
+    np.testing.assert_array_equal(a.bank.stats(), b.bank.stats())
 
 
 @pytest.mark.parametrize("impl_name,impl", IMPLS, ids=[i[0] for i in IMPLS])
