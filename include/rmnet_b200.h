@@ -186,6 +186,21 @@ RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_
                            size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * One frame of the reference's loop body in ONE call (models/rmnet.py:414-432 minus the convolutions), batch 1:
+ *   rmnet_frame_regions_forward(prev_mask, flow)  ->  rmnet_bank_memorize(k4, v4, mem_rects[1..n])
+ *   ->  rmnet_bank_memory_read(q_key, q_val shared by all objects, cur_rects[1..n])  ->  mem_val [n_obj,1024,h,w]
+ *   boxes_out [4][K][4] i32 = mem_bboxes, mem_rects, cur_bboxes, cur_rects.  4 kernels + 1 memset (+1 on commit).
+ * ------------------------------------------------------------------------------------------- */
+RMNET_API int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask,
+                               const float *flow, int K, int H, int W, int sampler, float prob_threshold,
+                               int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t,
+                               int pad_b, const float *k4, const float *v4, const float *q_key,
+                               const float *q_val, int n_obj, int elem_format, int precision, int impl,
+                               int commit, int *boxes_out, float *mem_val, void *box_workspace,
+                               size_t box_workspace_bytes, void *read_workspace, size_t read_workspace_bytes,
+                               void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Literal MemoryReader.forward(m_key, m_val, q_key, q_val) -> mem_val   (models/rmnet.py:147-165)
  *   m_key [n,128,T,h,w], m_val [n,512,T,h,w], q_key [n,128,h,w], q_val [n,512,h,w] (contiguous f32)
  *   mem_val [n,1024,h,w].  Region-agnostic (dense): packs the inputs into a scratch bank inside

@@ -48,6 +48,9 @@ PROTOTYPES = {
     "rmnet_memory_read_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_bank_memory_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rmnet_frame_step": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "rmnet_memory_reader_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_memory_reader_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -7,95 +7,110 @@
 //       Z = number of masked memory cells (score exactly 0, value exactly 0: they only enter the denominator)
 //   out-of-region query:  every score is 0  =>  p = 1/M  =>  mem[c] = sum_j V_j[c] / M   (the bank's vsum)
 //   mem_val[o, 512 + c, pos] = q_val[c, pos] * att16(o, pos)                              (:358, :163)
-// HBM-bound: lanes run along cells (coalesced mem_val writes, coalesced partial reads along compact queries).
+// Memory / latency bound: lanes run along cells (coalesced mem_val writes, coalesced partial reads along compact
+// queries); one thread owns 32 channels of one cell so the per-cell statistics are computed once per 32 outputs,
+// the split weights are parked in shared memory and the partial loads are issued two splits x eight channels at a time.
 #include "common.cuh"
 
 namespace rmnet {
 namespace {
 
 constexpr int kMergeThreads = 128;
-constexpr int kChPerCta = 8;
+constexpr int kChPerCta = 32;
+constexpr int kGroup = 8;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_stride, const int *__restrict__ q_rects,
              int h, int w, int n_obj, int n_splits, const float *__restrict__ opart, const float *__restrict__ ml,
              int nq_pad, float *__restrict__ mem_val) {
+  __shared__ float s_w[READ_MAX_SPLITS][kMergeThreads];  // split weights of this thread's cell
+  __shared__ float s_uniform[kChPerCta];                 // sum(V)/M of the CTA's channels (out-of-region read)
   const int N = h * w;
   const int o = blockIdx.z;
   const int pos = blockIdx.x * kMergeThreads + threadIdx.x;
   const int c0 = blockIdx.y * kChPerCta;
-  if (pos >= N) return;
-  const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-  const int cy = pos / w, cx = pos - cy * w;
-  const bool in_q = cx >= qrect.x && cx <= qrect.y && cy >= qrect.z && cy <= qrect.w;
-  float *out = mem_val + (size_t)o * 2 * RMNET_CV * N + pos;
-
-  // q_val passthrough, channels 512..1023: v4e * att16 (literal multiply keeps the sign of zero like the reference)
-  {
-    const float att = in_q ? 1.0f : 0.0f;
-    const float *qv = q_val + (long long)o * q_obj_stride + pos;
-#pragma unroll 4
-    for (int c = c0; c < c0 + kChPerCta; ++c) out[(size_t)(RMNET_CV + c) * N] = __ldg(qv + (size_t)c * N) * att;
-  }
+  const int tid = threadIdx.x;
 
   const int *meta = bank.meta + o * 8;
   const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
   const int M = Z + meta[META_CELLS_C] + meta[META_CELLS_T];
-  const float *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
+  if (tid < kChPerCta) {
+    const float *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
+    s_uniform[tid] = (vs_c[c0 + tid] + vs_t[c0 + tid]) * (1.0f / (float)M);
+  }
+  __syncthreads();
+  if (pos >= N) return;
+
+  const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+  const int cy = pos / w, cx = pos - cy * w;
+  const bool in_q = cx >= qrect.x && cx <= qrect.y && cy >= qrect.z && cy <= qrect.w;
+  float *out = mem_val + ((size_t)o * 2 * RMNET_CV + c0) * N + pos;
+
+  // q_val passthrough, channels 512..1023: v4e * att16 (literal multiply keeps the sign of zero like the reference)
+  {
+    const float att = in_q ? 1.0f : 0.0f;
+    const float *qv = q_val + (long long)o * q_obj_stride + (size_t)c0 * N + pos;
+    float *oq = out + (size_t)RMNET_CV * N;
+#pragma unroll
+    for (int g = 0; g < kChPerCta; g += kGroup) {
+      float x[kGroup];
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) x[k] = __ldg(qv + (size_t)(g + k) * N);
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) oq[(size_t)(g + k) * N] = x[k] * att;
+    }
+  }
 
   if (!in_q) {
-    const float inv_m = 1.0f / (float)M;
-#pragma unroll 4
-    for (int c = c0; c < c0 + kChPerCta; ++c) out[(size_t)c * N] = (vs_c[c] + vs_t[c]) * inv_m;
+#pragma unroll 8
+    for (int k = 0; k < kChPerCta; ++k) out[(size_t)k * N] = s_uniform[k];
     return;
   }
+
   const int n = (cy - qrect.z) * (qrect.y - qrect.x + 1) + (cx - qrect.x);  // compact query index
   const int half = c0 / (RMNET_CV / 2);
   const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((size_t)o * 2 + half) * nq_pad + n;
   const size_t ml_stride = (size_t)n_obj * 2 * nq_pad;  // between consecutive splits
-  // Single pass over the splits, four per round with every load of the round issued before use (the kernel is
-  // latency bound).  Online max: the running numerators / denominator are rescaled when a round raises it.
-  // Loads of the partial numerators are unconditional -- a split that saw no cells (max = -inf) left them
-  // unwritten, so its values are discarded by selection, never multiplied.
-  float m_run = Z > 0 ? 0.f : -INFINITY;
-  float L = Z > 0 ? (float)Z : 0.f;  // Z * 2^(0 - m_run) with m_run = 0
-  float num[kChPerCta];
-#pragma unroll
-  for (int k = 0; k < kChPerCta; ++k) num[k] = 0.f;
-  const size_t op_stride = (size_t)n_obj * RMNET_CV * nq_pad;
-  const float *op0 = opart + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
-  for (int s0 = 0; s0 < n_splits; s0 += 4) {
-    float2 st[4];
-    float v[4][kChPerCta];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int s = min(s0 + u, n_splits - 1);
-      st[u] = __ldg(mlp + (size_t)s * ml_stride);
-      if (s0 + u >= n_splits) st[u] = make_float2(-INFINITY, 0.f);
-#pragma unroll
-      for (int k = 0; k < kChPerCta; ++k) v[u][k] = __ldg(op0 + (size_t)s * op_stride + (size_t)k * nq_pad);
-    }
-    float m_new = m_run;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) m_new = fmaxf(m_new, st[u].x);
-    if (m_new == -INFINITY) continue;  // nothing seen so far
-    const float f = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_new);
-    L *= f;
-#pragma unroll
-    for (int k = 0; k < kChPerCta; ++k) num[k] *= f;
-    m_run = m_new;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (st[u].x == -INFINITY) continue;
-      const float wgt = exp2f(st[u].x - m_run);
-      L = fmaf(st[u].y, wgt, L);
-#pragma unroll
-      for (int k = 0; k < kChPerCta; ++k) num[k] = fmaf(v[u][k], wgt, num[k]);
-    }
+  // statistics of every split: reference max, then weights (parked in smem) and the denominator
+  float m_star = Z > 0 ? 0.f : -INFINITY;
+  for (int s = 0; s < n_splits; ++s) m_star = fmaxf(m_star, __ldg(mlp + (size_t)s * ml_stride).x);
+  float L = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
+  for (int s = 0; s < n_splits; ++s) {
+    const float2 st = __ldg(mlp + (size_t)s * ml_stride);
+    const float wgt = (st.x == -INFINITY) ? 0.f : ex2f(st.x - m_star);  // a split that saw no cells has undefined numerators
+    s_w[s][tid] = wgt;
+    L = fmaf(st.y, wgt, L);
   }
   const float inv_l = 1.0f / L;
+  const size_t op_stride = (size_t)n_obj * RMNET_CV * nq_pad;
+  const float *op0 = opart + ((size_t)o * RMNET_CV + c0) * nq_pad + n;
+#pragma unroll 1
+  for (int g = 0; g < kChPerCta; g += kGroup) {
+    float num[kGroup];
 #pragma unroll
-  for (int k = 0; k < kChPerCta; ++k) out[(size_t)(c0 + k) * N] = num[k] * inv_l;
+    for (int k = 0; k < kGroup; ++k) num[k] = 0.f;
+    const float *opg = op0 + (size_t)g * nq_pad;
+    for (int s = 0; s < n_splits; s += 2) {
+      const float w0 = s_w[s][tid], w1 = (s + 1 < n_splits) ? s_w[s + 1][tid] : 0.f;
+      const float *p0 = opg + (size_t)s * op_stride, *p1 = p0 + op_stride;
+      float v0[kGroup], v1[kGroup];
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) {
+        v0[k] = (w0 != 0.f) ? __ldg(p0 + (size_t)k * nq_pad) : 0.f;
+        v1[k] = (w1 != 0.f) ? __ldg(p1 + (size_t)k * nq_pad) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) num[k] = fmaf(v1[k], w1, fmaf(v0[k], w0, num[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < kGroup; ++k) out[(size_t)(g + k) * N] = num[k] * inv_l;
+  }
 }
 
 }  // namespace

@@ -85,6 +85,7 @@ class RegionalMemory:
         self.n = int(n_objects)
         self.precision, self.impl = precision, impl
         self.bank = ops.MemoryBank(self.n, self.h, self.w, max_frames, device, elem_format)
+        self._boxes = None
 
     def memorize(self, k4, v4, masks, commit):
         """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks [1,K,H,W]: the UNPADDED soft
@@ -103,13 +104,39 @@ class RegionalMemory:
 
 
     def step(self, k4, v4, prev_mask, flow, k4q, v4q, commit, out=None):
-        """One frame of the reference's loop body (models/rmnet.py:414-432 minus the convs) in 4 launches:
-        regions of both sides from ONE pass over prev_mask, pack k4/v4 (memorise), read for the current frame.
+        """One frame of the reference's loop body (models/rmnet.py:414-432 minus the convs) in ONE library call
+        (rmnet_frame_step: regions of both sides from one pass over prev_mask, pack k4/v4, regional read).
         Returns (m4 [n,1024,h,w], prev_bbox [1,K,4] padded coords, curr_bbox [1,K,4] raw coords)."""
-        mem_bb, mem_rects, cur_bb, cur_rects = ops.frame_regions(prev_mask, flow)
-        self.bank.memorize(k4, v4, mem_rects[0, 1:self.n + 1], commit)
-        m4 = self.bank.read(k4q, v4q, cur_rects[0, 1:self.n + 1], self.n, self.precision, self.impl, out=out)
-        return m4, mem_bb, cur_bb
+        bank = self.bank
+        for t, nm in ((k4, "k4"), (v4, "v4"), (prev_mask, "prev_mask"), (flow, "flow"), (k4q, "k4q"), (v4q, "v4q")):
+            ops._require(t, nm)
+        _, K, H, W = prev_mask.shape
+        if (H + self.lh + self.uh, W + self.lw + self.uw) != (self.Hp, self.Wp) or tuple(flow.shape) != (1, 2, H, W):
+            raise RuntimeError("prev_mask / flow shape mismatch")
+        if k4.shape[0] != self.n or k4q.numel() != 128 * self.h * self.w or v4q.numel() != 512 * self.h * self.w:
+            raise RuntimeError("k4 / k4q shape mismatch")
+        if bank.frames_committed + 1 > bank.max_frames:
+            raise RuntimeError(f"memory bank full: {bank.frames_committed} committed frames, capacity {bank.max_frames}")
+        dev = bank.device
+        if self._boxes is None or self._boxes.shape[1] != K:
+            self._boxes = torch.empty((4, K, 4), dtype=torch.int32, device=dev)
+        if out is None:
+            out = torch.empty((self.n, 1024, self.h, self.w), dtype=torch.float32, device=dev)
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        ws = ops._zero_ws(dev, 4096)
+        ops.check(ops.lib().rmnet_frame_step(
+            bank.ptr, bank.nbytes, bank.n_slots, bank.cap, prev_mask.data_ptr(), flow.data_ptr(), K, H, W,
+            ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, k4.data_ptr(), v4.data_ptr(),
+            k4q.data_ptr(), v4q.data_ptr(), self.n, bank.elem_format, self.precision, self.impl, 1 if commit else 0,
+            self._boxes.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), bank._ws_ptr, bank._ws.numel() - 1024,
+            torch.cuda.current_stream(dev).cuda_stream), "frame_step")
+        if commit:
+            bank.frames_committed += 1
+            bank.has_temp = False
+        else:
+            bank.has_temp = True
+        return out, self._boxes[0:1], self._boxes[2:3]
 
 
 def install(models_rmnet_module):
