@@ -97,7 +97,7 @@ struct ReadWorkspace {
   int n_splits, nq_pad;
   size_t total;
 };
-enum { READ_MAX_SPLITS = 32, KV_TILE = 64, MAX_TILES_PER_SPLIT = 64 };
+enum { READ_MAX_SPLITS = 16, KV_TILE = 64, MAX_TILES_PER_SPLIT = 64 };
 static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_splits) {
   ReadWorkspace W;
   W.nq_pad = cdiv(N, 128) * 128;
@@ -138,17 +138,6 @@ static inline int pick_splits(int n_obj, int N, int q_tile, int cap) {
   }
   return best;
 }
-#if defined(__CUDACC__)
-// device-side resolution of the split -> [tile_begin, tile_begin + n_it) for `count` stored cells
-__device__ __forceinline__ void split_range(int count, int n_splits, int split, int &tile_begin, int &n_it) {
-  const int n_tiles = (count + KV_TILE - 1) / KV_TILE;
-  int per = (n_tiles + n_splits - 1) / n_splits;
-  if (per < MIN_TILES_PER_SPLIT) per = MIN_TILES_PER_SPLIT;
-  tile_begin = split * per;
-  n_it = min(n_tiles, tile_begin + per) - tile_begin;
-  if (n_it < 0) n_it = 0;
-}
-#endif
 
 #ifdef __CUDACC__
 // 16-bit hi/lo split of an fp32 value.  fmt 0 = bf16, 1 = fp16.  x ~= hi + lo with |err| <= 2^-17|x| (bf16).
@@ -183,6 +172,56 @@ __device__ __forceinline__ int rect_pos(const int4 r, int i, int w) {
   int rw = r.y - r.x + 1;
   int cy = r.z + i / rw, cx = r.x + i % rw;
   return cy * w + cx;
+}
+// ---- stream-K schedule of the tcgen05 kernel (device side, from the actual cell counts) --------------------------
+// unit   = (object o, query tile qt of 128 compact queries, Cv half): nt(o) KV tiles of work; units are ordered
+//          (o, qt, half) and laid end to end on one axis of W = sum_o nqt(o) * 2 * nt(o) tile-units;
+// chunk  = c consecutive tile-units; persistent CTA g takes chunks g, g + G, ...; a chunk that crosses a unit
+//          boundary is processed as several pieces; piece j of a unit writes partial slot j (j < READ_MAX_SPLITS).
+// c balances the SMs (W / G), keeps the slot count per unit bounded and the accumulation chain short.
+enum { SCHED_MAX_OBJ = 64, UMMA_QT = 128 };
+struct SchedTable {
+  int nt[SCHED_MAX_OBJ];        // KV tiles of object o
+  int nqt[SCHED_MAX_OBJ];       // query tiles of object o
+  int base[SCHED_MAX_OBJ + 1];  // first tile-unit of object o
+  int chunk, n_chunks;
+};
+// called by one thread (or redundantly by all): fills the table for n_obj objects and G persistent CTAs
+__device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
+                                            int n_obj, int h, int w, int G) {
+  int acc = 0, max_wu = 0;
+  for (int o = 0; o < n_obj; ++o) {
+    const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+    const int nq = rect_cells(qr);
+    const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
+    T.nt[o] = (count + KV_TILE - 1) / KV_TILE;
+    T.nqt[o] = (nq + UMMA_QT - 1) / UMMA_QT;
+    T.base[o] = acc;
+    acc += T.nqt[o] * 2 * T.nt[o];
+    if (T.nqt[o] > 0) max_wu = max(max_wu, T.nt[o]);
+  }
+  T.base[n_obj] = acc;
+  int c = (acc + G - 1) / G;
+  if (c > MAX_TILES_PER_SPLIT) c = MAX_TILES_PER_SPLIT;                          // chain bound (accumulator truncation)
+  const int c_slots = (max_wu + READ_MAX_SPLITS - 2) / (READ_MAX_SPLITS - 1);    // <= READ_MAX_SPLITS pieces per unit
+  if (c < c_slots) c = c_slots;
+  if (c < 1) c = 1;
+  T.chunk = c;
+  T.n_chunks = (acc + c - 1) / c;
+}
+// number of partial slots a unit starting at tile-unit `ubase` with `nt` tiles was cut into
+__device__ __forceinline__ int sched_unit_pieces(int ubase, int nt, int c) {
+  return nt > 0 ? (ubase + nt - 1) / c - ubase / c + 1 : 0;
+}
+
+// device-side resolution of the split -> [tile_begin, tile_begin + n_it) for `count` stored cells
+__device__ __forceinline__ void split_range(int count, int n_splits, int split, int &tile_begin, int &n_it) {
+  const int n_tiles = (count + KV_TILE - 1) / KV_TILE;
+  int per = (n_tiles + n_splits - 1) / n_splits;
+  if (per < MIN_TILES_PER_SPLIT) per = MIN_TILES_PER_SPLIT;
+  tile_begin = split * per;
+  n_it = min(n_tiles, tile_begin + per) - tile_begin;
+  if (n_it < 0) n_it = 0;
 }
 #endif
 

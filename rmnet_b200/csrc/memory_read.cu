@@ -9,7 +9,8 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st);
 int launch_merge(const BankView &bank, const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h,
-                 int w, int n_splits, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
+                 int w, int n_splits, int sched_G, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
+int umma_grid_size();
 bool umma_supported(int cap_cells);
 
 namespace {
@@ -28,8 +29,7 @@ int rmnet_has_umma(void) { return umma_supported(64) ? 1 : 0; }
 
 size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells) {
   if (n_obj <= 0 || h <= 0 || w <= 0 || cap_cells <= 0) return 0;
-  const int s1 = pick_splits(n_obj, h * w, 64, cap_cells), s2 = pick_splits(n_obj, h * w, 128, cap_cells);
-  return read_workspace(nullptr, n_obj, h * w, s1 > s2 ? s1 : s2).total;
+  return read_workspace(nullptr, n_obj, h * w, READ_MAX_SPLITS).total;  // the stream-K kernel may cut a unit into that many pieces
 }
 
 int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
@@ -48,7 +48,7 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
   BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
   if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
   RMNET_CHECK_ARG(impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
-  const int n_splits = pick_splits(n_obj, h * w, impl == RMNET_IMPL_UMMA ? 128 : 64, cap_cells);
+  const int n_splits = impl == RMNET_IMPL_UMMA ? READ_MAX_SPLITS : pick_splits(n_obj, h * w, 64, cap_cells);
   ReadWorkspace W = read_workspace(workspace, n_obj, h * w, n_splits);
   if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
   RMNET_CHECK_ARG(stages >= 1 && stages <= 3, "bad stages mask %d", stages);
@@ -60,7 +60,7 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
     rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
   if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
   return launch_merge(bv, q_val, q_obj_stride ? (q_obj_stride / RMNET_CK) * RMNET_CV : 0, q_rects, n_obj, h, w, n_splits,
-                      W, mem_val, st);
+                      impl == RMNET_IMPL_UMMA ? umma_grid_size() : 0, W, mem_val, st);
 }
 
 

@@ -163,12 +163,43 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+struct Piece {
+  int o, qtile, half, tile_begin, n_it, slot;
+};
+// Enumerates the pieces of persistent CTA `cta` in a fixed order; every warp role walks the same sequence.
+struct PieceIter {
+  const SchedTable *T;
+  int n_obj, chunk, pos, hi, stride;
+  __device__ PieceIter(const SchedTable *t, int n_obj_, int cta, int n_ctas) : T(t), n_obj(n_obj_), chunk(cta), pos(0), hi(0), stride(n_ctas) {
+    chunk -= stride;
+  }
+  __device__ bool next(Piece &p) {
+    if (pos >= hi) {
+      chunk += stride;
+      if (chunk >= T->n_chunks) return false;
+      pos = chunk * T->chunk;
+      hi = min(T->base[n_obj], pos + T->chunk);
+    }
+    int o = 0;
+    while (T->base[o + 1] <= pos) ++o;  // objects with no work have base[o+1] == base[o] and are skipped
+    const int nt = T->nt[o];
+    const int rel = pos - T->base[o];
+    const int u = rel / nt, t0 = rel - u * nt;
+    const int len = min(hi - pos, nt - t0);
+    const int ubase = T->base[o] + u * nt;
+    p.o = o; p.qtile = u >> 1; p.half = u & 1; p.tile_begin = t0; p.n_it = len;
+    p.slot = chunk - ubase / T->chunk;
+    pos += len;
+    return true;
+  }
+};
+
 template <int FMT, bool USE_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
                         const int *__restrict__ bank_meta, const float *__restrict__ q_key, long long q_obj_stride,
-                        const int *__restrict__ q_rects, int h, int w, int n_splits,
+                        const int *__restrict__ q_rects, int h, int w,
                         float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj,
                         float *__restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
@@ -176,30 +207,16 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   Barriers *bars = reinterpret_cast<Barriers *>(smem_al + SMEM_TILES);
   const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
+  __shared__ SchedTable sched;
 
   const int N = h * w;
-  const int o = blockIdx.y;
-  const int half = blockIdx.z & 1, split = blockIdx.z >> 1;
-  const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-  const int nq = rect_cells(qrect);
-  const int q0 = blockIdx.x * QT;
-  if (q0 >= nq) return;  // uniform per CTA, before any barrier / TMEM allocation
-
-  const int *meta = bank_meta + o * 8;
-  const int count = meta[META_CELLS_C] + meta[META_CELLS_T];
-  int tile_begin, n_it;
-  split_range(count, n_splits, split, tile_begin, n_it);
-  if (n_it == 0) {  // surplus split (the grid is sized for the bank capacity): publish "saw nothing" and leave
-    if (threadIdx.x >= 128) {
-      float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)split * n_obj + o) * 2 + half) * nq_pad + q0 + (threadIdx.x - 128);
-      *dst = make_float2(-INFINITY, 0.f);
-    }
-    return;
-  }
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
-
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
+  __syncthreads();
+  if ((int)blockIdx.x >= sched.n_chunks) return;  // uniform per CTA, before any barrier / TMEM allocation
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
@@ -222,45 +239,54 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = bars->tmem_base;
+  PieceIter iter(&sched, n_obj, (int)blockIdx.x, (int)gridDim.x);
+  Piece pc;
 
   if (warp == 0) {
     // ================= key-tile TMA producer =================
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % KST;
-        mbar_wait(smem_u32(&bars->k_empty[s]), ((it / KST) & 1) ^ 1);
-        const uint32_t full = smem_u32(&bars->k_full[s]);
-        mbar_expect_tx(full, use_lo ? K_STAGE_BYTES : K_PLANE_BYTES);
-        const uint32_t dst = k_smem + s * K_STAGE_BYTES;
-        const int m0 = (tile_begin + it) * MT;
-        tma_load_3d(dst, &map_khi, full, 0, m0, o);
-        tma_load_3d(dst + K_PLANE_BYTES / 2, &map_khi, full, 64, m0, o);
-        if (use_lo) {
-          tma_load_3d(dst + K_PLANE_BYTES, &map_klo, full, 0, m0, o);
-          tma_load_3d(dst + K_PLANE_BYTES + K_PLANE_BYTES / 2, &map_klo, full, 64, m0, o);
+      int kt = 0;  // key tiles issued by this CTA so far (ring position / parity run across pieces)
+      while (iter.next(pc)) {
+        for (int it = 0; it < pc.n_it; ++it, ++kt) {
+          const int s = kt % KST;
+          mbar_wait(smem_u32(&bars->k_empty[s]), ((kt / KST) & 1) ^ 1);
+          const uint32_t full = smem_u32(&bars->k_full[s]);
+          mbar_expect_tx(full, use_lo ? K_STAGE_BYTES : K_PLANE_BYTES);
+          const uint32_t dst = k_smem + s * K_STAGE_BYTES;
+          const int m0 = (pc.tile_begin + it) * MT;
+          tma_load_3d(dst, &map_khi, full, 0, m0, pc.o);
+          tma_load_3d(dst + K_PLANE_BYTES / 2, &map_khi, full, 64, m0, pc.o);
+          if (use_lo) {
+            tma_load_3d(dst + K_PLANE_BYTES, &map_klo, full, 0, m0, pc.o);
+            tma_load_3d(dst + K_PLANE_BYTES + K_PLANE_BYTES / 2, &map_klo, full, 64, m0, pc.o);
+          }
         }
       }
     }
   } else if (warp == 2) {
     // ================= value-tile TMA producer =================
     if (lane == 0) {
-      for (int it = 0; it < n_it; ++it) {
-        const int s = it % VST;
-        mbar_wait(smem_u32(&bars->v_empty[s]), ((it / VST) & 1) ^ 1);
-        const uint32_t full = smem_u32(&bars->v_full[s]);
-        mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
-        const uint32_t dst = v_smem + s * V_STAGE_BYTES;
-        const int m0 = (tile_begin + it) * MT;
-        tma_load_3d(dst, &map_vhi, full, m0, half * CVH, o);
-        if (use_lo) tma_load_3d(dst + V_PLANE_BYTES, &map_vlo, full, m0, half * CVH, o);
+      int vt = 0;
+      while (iter.next(pc)) {
+        for (int it = 0; it < pc.n_it; ++it, ++vt) {
+          const int s = vt % VST;
+          mbar_wait(smem_u32(&bars->v_empty[s]), ((vt / VST) & 1) ^ 1);
+          const uint32_t full = smem_u32(&bars->v_full[s]);
+          mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
+          const uint32_t dst = v_smem + s * V_STAGE_BYTES;
+          const int m0 = (pc.tile_begin + it) * MT;
+          tma_load_3d(dst, &map_vhi, full, m0, pc.half * CVH, pc.o);
+          if (use_lo) tma_load_3d(dst + V_PLANE_BYTES, &map_vlo, full, m0, pc.half * CVH, pc.o);
+        }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc_qk = umma_idesc(fmt, MT), idesc_pv = umma_idesc(fmt, CVH);
-    auto issue_qk = [&](int it) {
-      const int s = it % KST, b = it & 1;
-      mbar_wait(smem_u32(&bars->k_full[s]), (it / KST) & 1);
+    int gt = 0;       // tiles whose score MMA has been issued (global over pieces: S/P buffer + key ring position)
+    auto issue_qk = [&]() {
+      const int s = gt % KST, b = gt & 1;
+      mbar_wait(smem_u32(&bars->k_full[s]), (gt / KST) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t kb = k_smem + s * K_STAGE_BYTES;
@@ -281,155 +307,169 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         umma_commit(smem_u32(&bars->s_full[b]));   // scores ready for the softmax warpgroup
       }
       __syncwarp();
+      ++gt;
     };
-    mbar_wait(smem_u32(&bars->q_ready), 0);
-    tc_fence_after();
-    if (n_it > 0) issue_qk(0);
-    if (n_it > 1) issue_qk(1);
-    for (int it = 0; it < n_it; ++it) {
-      const int s = it % VST, b = it & 1;
-      mbar_wait(smem_u32(&bars->p_full[b]), (it >> 1) & 1);
-      mbar_wait(smem_u32(&bars->v_full[s]), (it / VST) & 1);
+    int pt = 0;       // tiles whose P.V MMA has been issued (global)
+    int n_piece = 0;
+    while (iter.next(pc)) {
+      mbar_wait(smem_u32(&bars->q_ready), n_piece & 1);  // this piece's Q rows are in TMEM
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t vb = v_smem + s * V_STAGE_BYTES;
-        const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
+      ++n_piece;
+      const int gt_end = gt + pc.n_it;
+      issue_qk();
+      if (gt < gt_end) issue_qk();
+      for (int it = 0; it < pc.n_it; ++it, ++pt) {
+        const int s = pt % VST, b = pt & 1;
+        mbar_wait(smem_u32(&bars->p_full[b]), (pt >> 1) & 1);
+        mbar_wait(smem_u32(&bars->v_full[s]), (pt / VST) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t vb = v_smem + s * V_STAGE_BYTES;
+          const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
 #pragma unroll
-        for (int kk = 0; kk < MT / 16; ++kk) {
-          const uint64_t bh = umma_desc_sw128(vb + kk * 32);
-          umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
-          if (use_lo) {
-            const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
-            umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
-            umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+          for (int kk = 0; kk < MT / 16; ++kk) {
+            const uint64_t bh = umma_desc_sw128(vb + kk * 32);
+            umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
+            if (use_lo) {
+              const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
+              umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
+              umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+            }
           }
+          umma_commit(smem_u32(&bars->v_empty[s]));
+          umma_commit(smem_u32(&bars->pv_done[b]));
         }
-        umma_commit(smem_u32(&bars->v_empty[s]));
-        umma_commit(smem_u32(&bars->pv_done[b]));
+        __syncwarp();
+        if (gt < gt_end) issue_qk();  // overwrites the S/P buffer PV(it) just consumed: in-order on the tensor pipe
       }
-      __syncwarp();
-      if (it + 2 < n_it) issue_qk(it + 2);  // overwrites the S/P buffer PV(it) just consumed: in-order on the tensor pipe
     }
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue warpgroup: thread <-> query row <-> TMEM lane =================
     const int row = threadIdx.x - 128;                  // 0..127
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t t_base = tmem + lane_base;
-    const int n = q0 + row;
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
+    int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
+    bool first_piece = true;
+    while (iter.next(pc)) {
+      const int o = pc.o;
+      const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+      const int nq = rect_cells(qrect);
+      const int n = pc.qtile * QT + row;
+      const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
 
-    // ---- Q rows -> 16-bit hi/lo planes in TMEM (A operand of the score product), 32 channels per pass
-    {
-      const bool live = n < nq;
-      const float *qp = q_key + (long long)o * q_obj_stride + (live ? rect_pos(qrect, n, w) : 0);
+      // ---- Q rows -> 16-bit hi/lo planes in TMEM (A operand of the score product).  All score MMAs of the previous
+      //      piece have retired: its last softmax pass waited on their commit.
+      {
+        const bool live = n < nq;
+        const float *qp = q_key + (long long)o * q_obj_stride + (live ? rect_pos(qrect, n, w) : 0);
 #pragma unroll 1
-      for (int c0 = 0; c0 < RMNET_CK; c0 += 64) {  // 64 strided loads in flight per thread per pass
-        float xq[64];
+        for (int c0 = 0; c0 < RMNET_CK; c0 += 64) {  // 64 strided loads in flight per thread per pass
+          float xq[64];
 #pragma unroll
-        for (int j = 0; j < 64; ++j) xq[j] = live ? __ldg(qp + (long long)(c0 + j) * N) : 0.f;
-        uint32_t hi[32], lo[32];
+          for (int j = 0; j < 64; ++j) xq[j] = live ? __ldg(qp + (long long)(c0 + j) * N) : 0.f;
+          uint32_t hi[32], lo[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          lo[j] = 0;
-          split_pack2<FMT, USE_LO>(xq[2 * j], xq[2 * j + 1], hi[j], lo[j]);
+          for (int j = 0; j < 32; ++j) {
+            lo[j] = 0;
+            split_pack2<FMT, USE_LO>(xq[2 * j], xq[2 * j + 1], hi[j], lo[j]);
+          }
+          TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
+          TMEM_ST16(t_base + TM_Q_HI + c0 / 2 + 16, hi, 16);
+          if (USE_LO) {
+            TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
+            TMEM_ST16(t_base + TM_Q_LO + c0 / 2 + 16, lo, 16);
+          }
         }
-        TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
-        TMEM_ST16(t_base + TM_Q_HI + c0 / 2 + 16, hi, 16);
-        if (USE_LO) {
-          TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
-          TMEM_ST16(t_base + TM_Q_LO + c0 / 2 + 16, lo, 16);
-        }
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->q_ready));
       }
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->q_ready));
-    }
 
-    float m_ref = -INFINITY, l_sum = 0.f;
-    for (int it = 0; it < n_it; ++it) {
-      const int b = it & 1;
-      const uint32_t s_addr = t_base + TM_S0 + b * MT;
-      mbar_wait(smem_u32(&bars->s_full[b]), (it >> 1) & 1);
-      tc_fence_after();
-      uint32_t sr[MT];
-      TMEM_LD16(s_addr, sr, 0);
-      TMEM_LD16(s_addr + 16, sr, 16);
-      TMEM_LD16(s_addr + 32, sr, 32);
-      TMEM_LD16(s_addr + 48, sr, 48);
-      tc_wait_ld();
-      if (dbg && it == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-#pragma unroll
-        for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
-      }
-      const int valid = count - (tile_begin + it) * MT;  // columns >= valid are beyond the stored cells (last tile only)
-      if (valid < MT) {
-#pragma unroll
-        for (int j = 0; j < MT; ++j) if (j >= valid) sr[j] = 0xff800000u;  // -inf
-      }
-      float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
-#pragma unroll
-      for (int j = 2; j < MT; j += 2) {
-        mx0 = fmaxf(mx0, __uint_as_float(sr[j]));
-        mx1 = fmaxf(mx1, __uint_as_float(sr[j + 1]));
-      }
-      const float mx = fmaxf(mx0, mx1) * scale;  // scale > 0: max commutes with the scaling
-      if (it == 0) {
-        m_ref = (mx == -INFINITY) ? 0.f : mx;
-      } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
-        // lazy rescale of the O accumulator (rare after the first tiles): PV(it-1) must have retired, PV(it) cannot
-        // start before this warp arrives on p_full below.
-        mbar_wait(smem_u32(&bars->pv_done[(it - 1) & 1]), ((it - 1) >> 1) & 1);
+      float m_ref = -INFINITY, l_sum = 0.f;
+      for (int it = 0; it < pc.n_it; ++it, ++gt) {
+        const int b = gt & 1;
+        const uint32_t s_addr = t_base + TM_S0 + b * MT;
+        mbar_wait(smem_u32(&bars->s_full[b]), (gt >> 1) & 1);
         tc_fence_after();
-        const float m_new = fmaxf(m_ref, mx);
-        const float f = exp2f(m_ref - m_new);
+        uint32_t sr[MT];
+        TMEM_LD16(s_addr, sr, 0);
+        TMEM_LD16(s_addr + 16, sr, 16);
+        TMEM_LD16(s_addr + 32, sr, 32);
+        TMEM_LD16(s_addr + 48, sr, 48);
+        tc_wait_ld();
+        if (dbg && first_piece && it == 0 && blockIdx.x == 0) {
+#pragma unroll
+          for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
+        }
+        const int valid = count - (pc.tile_begin + it) * MT;  // columns >= valid are beyond the stored cells (last tile only)
+        if (valid < MT) {
+#pragma unroll
+          for (int j = 0; j < MT; ++j) if (j >= valid) sr[j] = 0xff800000u;  // -inf
+        }
+        float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
+#pragma unroll
+        for (int j = 2; j < MT; j += 2) {
+          mx0 = fmaxf(mx0, __uint_as_float(sr[j]));
+          mx1 = fmaxf(mx1, __uint_as_float(sr[j + 1]));
+        }
+        const float mx = fmaxf(mx0, mx1) * scale;  // scale > 0: max commutes with the scaling
+        if (it == 0) {
+          m_ref = (mx == -INFINITY) ? 0.f : mx;
+        } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
+          // lazy rescale of the O accumulator (rare after the first tiles): PV(it-1) must have retired, PV(it) cannot
+          // start before this warp arrives on p_full below.
+          mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
+          tc_fence_after();
+          const float m_new = fmaxf(m_ref, mx);
+          const float f = exp2f(m_ref - m_new);
 #pragma unroll 1
-        for (int c = 0; c < CVH; c += 32) {
-          uint32_t orr[32];
-          TMEM_LD16(t_base + TM_O + c, orr, 0);
-          TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
-          tc_wait_ld();
+          for (int c = 0; c < CVH; c += 32) {
+            uint32_t orr[32];
+            TMEM_LD16(t_base + TM_O + c, orr, 0);
+            TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
+            tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * f);
-          TMEM_ST16(t_base + TM_O + c, orr, 0);
-          TMEM_ST16(t_base + TM_O + c + 16, orr, 16);
+            for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * f);
+            TMEM_ST16(t_base + TM_O + c, orr, 0);
+            TMEM_ST16(t_base + TM_O + c + 16, orr, 16);
+          }
+          l_sum *= f;
+          m_ref = m_new;
         }
-        l_sum *= f;
-        m_ref = m_new;
-      }
-      // P = 2^(s*scale - m_ref): one FFMA + one MUFU per element, then the 16-bit hi/lo split (packed cvt), stored
-      // two cells per TMEM column over the S buffer: hi plane in columns [0,32), lo plane in [32,64)
-      const float neg_m = -m_ref;
-      float l0 = 0.f, l1 = 0.f;
+        // P = 2^(s*scale - m_ref): one FFMA + one MUFU per element, then the 16-bit hi/lo split (packed cvt), stored
+        // two cells per TMEM column over the S buffer: hi plane in columns [0,32), lo plane in [32,64)
+        const float neg_m = -m_ref;
+        float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-      for (int c = 0; c < MT; c += 16) {
-        uint32_t ph[8], pl[8];
+        for (int c = 0; c < MT; c += 16) {
+          uint32_t ph[8], pl[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j]), scale, neg_m));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j + 1]), scale, neg_m));
-          l0 += p0;
-          l1 += p1;
-          pl[j] = 0;
-          split_pack2<FMT, USE_LO>(p0, p1, ph[j], pl[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j]), scale, neg_m));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[c + 2 * j + 1]), scale, neg_m));
+            l0 += p0;
+            l1 += p1;
+            pl[j] = 0;
+            split_pack2<FMT, USE_LO>(p0, p1, ph[j], pl[j]);
+          }
+          TMEM_ST8(s_addr + c / 2, ph, 0);
+          if (USE_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
         }
-        TMEM_ST8(s_addr + c / 2, ph, 0);
-        if (USE_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
+        l_sum += l0 + l1;
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->p_full[b]));
       }
-      l_sum += l0 + l1;
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->p_full[b]));
-    }
 
-    // ---- epilogue: unnormalised numerators + (max, sum) statistics for merge.cu
-    {
-      float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)split * n_obj + o) * 2 + half) * nq_pad + n;
-      *dst = make_float2(n_it > 0 ? m_ref : -INFINITY, l_sum);
-    }
-    if (n_it > 0) {
-      mbar_wait(smem_u32(&bars->pv_done[(n_it - 1) & 1]), ((n_it - 1) >> 1) & 1);
+      // ---- epilogue of the piece: unnormalised numerators + (max, sum) statistics for merge.cu, partial slot pc.slot
+      {
+        float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)pc.slot * n_obj + o) * 2 + pc.half) * nq_pad + n;
+        *dst = make_float2(m_ref, l_sum);
+      }
+      mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
       tc_fence_after();
-      float *ob = opart + (((size_t)split * n_obj + o) * RMNET_CV + half * CVH) * nq_pad + n;
+      float *ob = opart + (((size_t)pc.slot * n_obj + o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
 #pragma unroll 1
       for (int c = 0; c < CVH; c += 32) {
         uint32_t orr[32];
@@ -439,7 +479,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) ob[(size_t)(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
       }
-      if (dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) dbg[QT * MT + row] = m_ref;
+      if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
+      first_piece = false;
     }
   }
 
@@ -488,10 +529,22 @@ thread_local float *g_dbg = nullptr;
 
 bool umma_supported(int cap_cells) { return cap_cells % 64 == 0; }
 
+// persistent grid: one CTA per SM (224 KB of dynamic smem => 1 CTA/SM); merge.cu rebuilds the same schedule from it
+int umma_grid_size() {
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n_sms = v;
+    else n_sms = 148;
+  }
+  return n_sms;
+}
+
 int launch_memory_read_umma(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st) {
   RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
+  RMNET_CHECK_ARG(n_obj <= SCHED_MAX_OBJ, "tcgen05 path supports at most %d objects per call", (int)SCHED_MAX_OBJ);
   CUtensorMap mkh, mkl, mvh, mvl;
   const uint64_t cap = bank.cap, ns = bank.n_slots;
   int rc;
@@ -500,15 +553,16 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
   if ((rc = make_map(&mkl, bank.klo, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
   if ((rc = make_map(&mvh, bank.vhi, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
   if ((rc = make_map(&mvl, bank.vlo, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
-  dim3 grid(cdiv(h * w, QT), n_obj, 2 * n_splits);
+  const int n_sms = umma_grid_size();
+  dim3 grid(n_sms);
+  (void)n_splits;
   const bool lo = precision == RMNET_PREC_SPLIT3;
 #define RMNET_LAUNCH_UMMA(F, L)                                                                                          \
   do {                                                                                                                   \
     RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                     (int)SMEM_BYTES));                                                                   \
     memory_read_umma_kernel<F, L><<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, \
-                                                                      q_rects, h, w, n_splits, W.opart, W.ml, W.nq_pad, \
-                                                                      n_obj, g_dbg);                                     \
+                                                                      q_rects, h, w, W.opart, W.ml, W.nq_pad, n_obj, g_dbg); \
   } while (0)
   if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
   else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);
