@@ -94,6 +94,7 @@ static inline BankView bank_view(void *bank, int n_slots, int cap) {
 // opart [n_splits][n_obj][512][nq_pad] f32 (unnormalised numerators), ml [n_splits][n_obj][2 halves][nq_pad][2] f32
 struct ReadWorkspace {
   float *opart, *ml;
+  int *sched;  // [SCHED_MAX_OBJ] partial slots per object, written by the tcgen05 kernel for merge.cu
   int n_splits, nq_pad;
   size_t total;
 };
@@ -107,6 +108,8 @@ static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_spl
   o = align_up(o + (size_t)W.n_splits * n_obj * RMNET_CV * W.nq_pad * sizeof(float), 1024);
   W.ml = (float *)((char *)ws + o);
   o = align_up(o + (size_t)W.n_splits * n_obj * 2 * W.nq_pad * 2 * sizeof(float), 1024);
+  W.sched = (int *)((char *)ws + o);
+  o = align_up(o + 64 * sizeof(int), 1024);
   W.total = o;
   return W;
 }
@@ -173,45 +176,69 @@ __device__ __forceinline__ int rect_pos(const int4 r, int i, int w) {
   int cy = r.z + i / rw, cx = r.x + i % rw;
   return cy * w + cx;
 }
-// ---- stream-K schedule of the tcgen05 kernel (device side, from the actual cell counts) --------------------------
-// unit   = (object o, query tile qt of 128 compact queries, Cv half): nt(o) KV tiles of work; units are ordered
-//          (o, qt, half) and laid end to end on one axis of W = sum_o nqt(o) * 2 * nt(o) tile-units;
-// chunk  = c consecutive tile-units; persistent CTA g takes chunks g, g + G, ...; a chunk that crosses a unit
-//          boundary is processed as several pieces; piece j of a unit writes partial slot j (j < READ_MAX_SPLITS).
-// c balances the SMs (W / G), keeps the slot count per unit bounded and the accumulation chain short.
+// ---- work schedule of the persistent tcgen05 kernel (device side, from the actual cell counts) ----------------------
+// item = (object o, KV chunk j of ns(o), Cv half, query tile qt): a balanced 1/ns(o) share of the object's nt(o) KV
+// tiles for 128 compact queries.  Items are ordered (o, j, half, qt) with qt fastest and dealt round-robin to the
+// persistent CTAs, so CTAs that run side by side stream the SAME key/value tiles (one DRAM fetch, L2 hits for the rest).
+// ns(o) = ceil(nt(o) / c); the chunk length c is chosen among max_nt / k, k = 1..READ_MAX_SPLITS, to minimise
+// rounds(c) * c  (rounds = ceil(#items / #CTAs)), subject to the accumulation-chain bound c <= MAX_TILES_PER_SPLIT.
 enum { SCHED_MAX_OBJ = 64, UMMA_QT = 128 };
 struct SchedTable {
-  int nt[SCHED_MAX_OBJ];        // KV tiles of object o
-  int nqt[SCHED_MAX_OBJ];       // query tiles of object o
-  int base[SCHED_MAX_OBJ + 1];  // first tile-unit of object o
-  int chunk, n_chunks;
+  int nt[SCHED_MAX_OBJ];         // KV tiles of object o
+  int nqt[SCHED_MAX_OBJ];        // query tiles of object o
+  int ns[SCHED_MAX_OBJ];         // KV chunks (= partial slots) of object o
+  int ibase[SCHED_MAX_OBJ + 1];  // first item of object o
 };
-// called by one thread (or redundantly by all): fills the table for n_obj objects and G persistent CTAs
+// Called by ONE FULL WARP (all 32 lanes); lane 0 writes the table.  G = number of persistent CTAs.
 __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
                                             int n_obj, int h, int w, int G) {
-  int acc = 0, max_wu = 0;
-  for (int o = 0; o < n_obj; ++o) {
-    const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-    const int nq = rect_cells(qr);
-    const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
-    T.nt[o] = (count + KV_TILE - 1) / KV_TILE;
-    T.nqt[o] = (nq + UMMA_QT - 1) / UMMA_QT;
-    T.base[o] = acc;
-    acc += T.nqt[o] * 2 * T.nt[o];
-    if (T.nqt[o] > 0) max_wu = max(max_wu, T.nt[o]);
+  const int lane = threadIdx.x & 31;
+  // per-object tile counts (lanes over objects), also kept in registers for the candidate evaluation
+  int max_nt = 0;
+  for (int o0 = 0; o0 < n_obj; o0 += 32) {
+    const int o = o0 + lane;
+    int nt = 0, nqt = 0;
+    if (o < n_obj) {
+      const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+      const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
+      nt = (count + KV_TILE - 1) / KV_TILE;
+      nqt = (rect_cells(qr) + UMMA_QT - 1) / UMMA_QT;
+      T.nt[o] = nt;
+      T.nqt[o] = nqt;
+    }
+    max_nt = max(max_nt, __reduce_max_sync(0xffffffffu, nqt > 0 ? nt : 0));
   }
-  T.base[n_obj] = acc;
-  int c = (acc + G - 1) / G;
-  if (c > MAX_TILES_PER_SPLIT) c = MAX_TILES_PER_SPLIT;                          // chain bound (accumulator truncation)
-  const int c_slots = (max_wu + READ_MAX_SPLITS - 2) / (READ_MAX_SPLITS - 1);    // <= READ_MAX_SPLITS pieces per unit
-  if (c < c_slots) c = c_slots;
-  if (c < 1) c = 1;
-  T.chunk = c;
-  T.n_chunks = (acc + c - 1) / c;
-}
-// number of partial slots a unit starting at tile-unit `ubase` with `nt` tiles was cut into
-__device__ __forceinline__ int sched_unit_pieces(int ubase, int nt, int c) {
-  return nt > 0 ? (ubase + nt - 1) / c - ubase / c + 1 : 0;
+  __syncwarp();
+  // candidate k (lane): c = ceil(max_nt / k)
+  const int k = lane + 1;
+  int c = max_nt > 0 ? (max_nt + k - 1) / k : 1;
+  long long cost = 0x7fffffffffffffffLL;
+  if (k <= READ_MAX_SPLITS && (c <= MAX_TILES_PER_SPLIT || k == READ_MAX_SPLITS)) {
+    long long items = 0;
+    for (int o = 0; o < n_obj; ++o) {
+      const int nt = T.nt[o];
+      if (nt > 0 && T.nqt[o] > 0) items += (long long)((nt + c - 1) / c) * 2 * T.nqt[o];
+    }
+    const long long rounds = (items + G - 1) / G;
+    cost = rounds * (long long)(c + 6) * 64 + k;  // +6: per-item prologue/epilogue in tile units; ties -> fewer chunks
+  }
+  long long best = cost;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
+  const unsigned who = __ballot_sync(0xffffffffu, cost == best);
+  c = __shfl_sync(0xffffffffu, c, __ffs(who) - 1);
+  if (lane == 0) {
+    int acc = 0;
+    for (int o = 0; o < n_obj; ++o) {
+      const int nt = T.nt[o];
+      const int ns = (nt > 0 && T.nqt[o] > 0) ? (nt + c - 1) / c : 0;
+      T.ns[o] = ns;
+      T.ibase[o] = acc;
+      acc += ns * 2 * T.nqt[o];
+    }
+    T.ibase[n_obj] = acc;
+  }
+  __syncwarp();
 }
 
 // device-side resolution of the split -> [tile_begin, tile_begin + n_it) for `count` stored cells

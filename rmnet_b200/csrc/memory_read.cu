@@ -9,8 +9,7 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st);
 int launch_merge(const BankView &bank, const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h,
-                 int w, int n_splits, int sched_G, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
-int umma_grid_size();
+                 int w, int n_splits, bool device_sched, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
 bool umma_supported(int cap_cells);
 
 namespace {
@@ -60,7 +59,7 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
     rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
   if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
   return launch_merge(bv, q_val, q_obj_stride ? (q_obj_stride / RMNET_CK) * RMNET_CV : 0, q_rects, n_obj, h, w, n_splits,
-                      impl == RMNET_IMPL_UMMA ? umma_grid_size() : 0, W, mem_val, st);
+                      impl == RMNET_IMPL_UMMA, W, mem_val, st);
 }
 
 

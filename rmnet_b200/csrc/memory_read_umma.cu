@@ -166,30 +166,25 @@ struct Barriers {
 struct Piece {
   int o, qtile, half, tile_begin, n_it, slot;
 };
-// Enumerates the pieces of persistent CTA `cta` in a fixed order; every warp role walks the same sequence.
+// Enumerates the work items of persistent CTA `cta` (items cta, cta + n_ctas, ...); every warp role walks the same sequence.
 struct PieceIter {
   const SchedTable *T;
-  int n_obj, chunk, pos, hi, stride;
-  __device__ PieceIter(const SchedTable *t, int n_obj_, int cta, int n_ctas) : T(t), n_obj(n_obj_), chunk(cta), pos(0), hi(0), stride(n_ctas) {
-    chunk -= stride;
-  }
+  int n_obj, item, stride;
+  __device__ PieceIter(const SchedTable *t, int n_obj_, int cta, int n_ctas) : T(t), n_obj(n_obj_), item(cta - n_ctas), stride(n_ctas) {}
   __device__ bool next(Piece &p) {
-    if (pos >= hi) {
-      chunk += stride;
-      if (chunk >= T->n_chunks) return false;
-      pos = chunk * T->chunk;
-      hi = min(T->base[n_obj], pos + T->chunk);
-    }
+    item += stride;
+    if (item >= T->ibase[n_obj]) return false;
     int o = 0;
-    while (T->base[o + 1] <= pos) ++o;  // objects with no work have base[o+1] == base[o] and are skipped
-    const int nt = T->nt[o];
-    const int rel = pos - T->base[o];
-    const int u = rel / nt, t0 = rel - u * nt;
-    const int len = min(hi - pos, nt - t0);
-    const int ubase = T->base[o] + u * nt;
-    p.o = o; p.qtile = u >> 1; p.half = u & 1; p.tile_begin = t0; p.n_it = len;
-    p.slot = chunk - ubase / T->chunk;
-    pos += len;
+    while (T->ibase[o + 1] <= item) ++o;  // objects without work own no items and are skipped
+    int r = item - T->ibase[o];
+    const int nqt = T->nqt[o], nt = T->nt[o], ns = T->ns[o];
+    p.o = o;
+    p.qtile = r % nqt; r /= nqt;
+    p.half = r & 1;
+    const int j = r >> 1;
+    p.slot = j;
+    p.tile_begin = (int)(((long long)j * nt) / ns);           // balanced partition of the nt tiles into ns chunks
+    p.n_it = (int)(((long long)(j + 1) * nt) / ns) - p.tile_begin;
     return true;
   }
 };
@@ -200,8 +195,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
                         const int *__restrict__ bank_meta, const float *__restrict__ q_key, long long q_obj_stride,
                         const int *__restrict__ q_rects, int h, int w,
-                        float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj,
-                        float *__restrict__ dbg) {
+                        float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
+                        int n_obj, float *__restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -214,9 +209,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   constexpr bool use_lo = USE_LO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (threadIdx.x == 0) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
+  if (warp == 0) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
   __syncthreads();
-  if ((int)blockIdx.x >= sched.n_chunks) return;  // uniform per CTA, before any barrier / TMEM allocation
+  if (blockIdx.x == 0 && threadIdx.x < n_obj) sched_out[threadIdx.x] = sched.ns[threadIdx.x];  // for merge.cu
+  if ((int)blockIdx.x >= sched.ibase[n_obj]) return;  // uniform per CTA, before any barrier / TMEM allocation
 
   // ---- one-time setup
   if (warp == 0 && lane == 0) {
@@ -562,7 +558,7 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
     RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                     (int)SMEM_BYTES));                                                                   \
     memory_read_umma_kernel<F, L><<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, \
-                                                                      q_rects, h, w, W.opart, W.ml, W.nq_pad, n_obj, g_dbg); \
+                                                                      q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj, g_dbg); \
   } while (0)
   if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
   else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);

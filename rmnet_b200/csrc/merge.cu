@@ -27,11 +27,10 @@ __device__ __forceinline__ float ex2f(float x) {
 
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_stride, const int *__restrict__ q_rects,
-             int h, int w, int n_obj, int n_splits, int sched_G, const float *__restrict__ opart,
+             int h, int w, int n_obj, int n_splits, const int *__restrict__ sched_ns, const float *__restrict__ opart,
              const float *__restrict__ ml, int nq_pad, float *__restrict__ mem_val) {
   __shared__ float s_w[READ_MAX_SPLITS][kMergeThreads];  // split weights of this thread's cell
   __shared__ float s_uniform[kChPerCta];                 // sum(V)/M of the CTA's channels (out-of-region read)
-  __shared__ SchedTable sched;                           // stream-K schedule of the tcgen05 kernel (sched_G > 0)
   const int N = h * w;
   const int o = blockIdx.z;
   const int pos = blockIdx.x * kMergeThreads + threadIdx.x;
@@ -41,7 +40,6 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   const int *meta = bank.meta + o * 8;
   const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
   const int M = Z + meta[META_CELLS_C] + meta[META_CELLS_T];
-  if (sched_G > 0 && tid == kMergeThreads - 1) sched_build(sched, bank.meta, q_rects, n_obj, h, w, sched_G);
   if (tid < kChPerCta) {
     const float *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
     s_uniform[tid] = (vs_c[c0 + tid] + vs_t[c0 + tid]) * (1.0f / (float)M);
@@ -77,10 +75,7 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
 
   const int n = (cy - qrect.z) * (qrect.y - qrect.x + 1) + (cx - qrect.x);  // compact query index
   const int half = c0 / (RMNET_CV / 2);
-  if (sched_G > 0) {  // the tcgen05 kernel cut this cell's unit (object, query tile, Cv half) into exactly this many pieces
-    const int nt = sched.nt[o];
-    n_splits = sched_unit_pieces(sched.base[o] + ((n / UMMA_QT) * 2 + half) * nt, nt, sched.chunk);
-  }
+  if (sched_ns) n_splits = __ldg(sched_ns + o);  // KV chunks the persistent tcgen05 kernel used for this object
   const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((size_t)o * 2 + half) * nq_pad + n;
   const size_t ml_stride = (size_t)n_obj * 2 * nq_pad;  // between consecutive splits
   // statistics of every split: reference max, then weights (parked in smem) and the denominator
@@ -122,9 +117,9 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
 }  // namespace
 
 int launch_merge(const BankView &bank, const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h,
-                 int w, int n_splits, int sched_G, const ReadWorkspace &W, float *mem_val, cudaStream_t st) {
+                 int w, int n_splits, bool device_sched, const ReadWorkspace &W, float *mem_val, cudaStream_t st) {
   dim3 grid(cdiv(h * w, kMergeThreads), RMNET_CV / kChPerCta, n_obj);
-  merge_kernel<<<grid, kMergeThreads, 0, st>>>(bank, q_val, q_obj_stride, q_rects, h, w, n_obj, n_splits, sched_G, W.opart,
+  merge_kernel<<<grid, kMergeThreads, 0, st>>>(bank, q_val, q_obj_stride, q_rects, h, w, n_obj, n_splits, device_sched ? W.sched : nullptr, W.opart,
                                                W.ml, W.nq_pad, mem_val);
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
