@@ -24,6 +24,11 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
+// CTA = 128 cells x 32 channels of one object.
+//   phase A (fill): thread = VEC consecutive cells x 8 channels, 128-bit accesses: q_val passthrough (all cells) and
+//                   the uniform rows (out-of-region cells only);
+//   phase B (gather): thread = ONE in-region cell x 32 channels: statistics of all splits in one batch of loads,
+//                   then the partial numerators two splits x eight channels at a time (independent loads in flight).
 template <int VEC>
 __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_stride, const int *__restrict__ q_rects,
@@ -34,9 +39,6 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   const int o = blockIdx.z;
   const int c0 = blockIdx.y * kChPerCta;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, cl = tid >> 5;
-  const int p0 = (blockIdx.x * 32 + lane) * VEC;  // first cell of this thread
-  const int ck = c0 + cl * kChPerThread;          // first channel of this thread
 
   const int *meta = bank.meta + o * 8;
   const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
@@ -45,92 +47,115 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
     const float *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
     s_uniform[tid] = (vs_c[c0 + tid] + vs_t[c0 + tid]) * (1.0f / (float)M);
   }
-  __syncthreads();
-  if (p0 >= N) return;
-
   const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
   const int rw = qrect.y - qrect.x + 1;
-  bool in_q[VEC];
-  int nidx[VEC];
-  bool any_in = false;
-#pragma unroll
-  for (int e = 0; e < VEC; ++e) {
-    const int pos = p0 + e;
-    const int cy = pos / w, cx = pos - cy * w;
-    in_q[e] = pos < N && cx >= qrect.x && cx <= qrect.y && cy >= qrect.z && cy <= qrect.w;
-    nidx[e] = (cy - qrect.z) * rw + (cx - qrect.x);  // compact query index
-    any_in |= in_q[e];
-  }
-  const unsigned obase = (unsigned)o * 2u * RMNET_CV * (unsigned)N;
-  float *out = mem_val + obase + (unsigned)ck * (unsigned)N + p0;
+  const unsigned uN = (unsigned)N;
+  float *out_o = mem_val + (unsigned)o * 2u * RMNET_CV * uN;
+  __syncthreads();
 
-  // ---- q_val passthrough, channels 512..1023: v4e * att16 (literal multiply keeps the sign of zero like the reference)
+  // ------------------------------ phase A: fill ------------------------------
   {
-    const float *qv = q_val + (long long)o * q_obj_stride + (unsigned)ck * (unsigned)N + p0;
-    float *oq = out + (unsigned)RMNET_CV * (unsigned)N;
-    if (VEC == 4) {
-      float4 x[kChPerThread];
+    const int lane = tid & 31, cl = tid >> 5;
+    const int p0 = blockIdx.x * 128 + lane * VEC;  // first cell of this thread (128 cells per CTA; VEC = 1 covers them in 4 passes)
+#pragma unroll 1
+    for (int pass = 0; pass < (VEC == 4 ? 1 : 4); ++pass) {
+      const int pa = p0 + pass * 32;
+      if (pa >= N) break;
+      const int ck = c0 + cl * kChPerThread;
+      bool in_q[VEC];
+      bool any_in = false;
 #pragma unroll
-      for (int k = 0; k < kChPerThread; ++k) x[k] = __ldg(reinterpret_cast<const float4 *>(qv + (unsigned)k * (unsigned)N));
-#pragma unroll
-      for (int k = 0; k < kChPerThread; ++k) {
-        x[k].x *= in_q[0] ? 1.0f : 0.0f; x[k].y *= in_q[1 % VEC] ? 1.0f : 0.0f;
-        x[k].z *= in_q[2 % VEC] ? 1.0f : 0.0f; x[k].w *= in_q[3 % VEC] ? 1.0f : 0.0f;
-        *reinterpret_cast<float4 *>(oq + (unsigned)k * (unsigned)N) = x[k];
+      for (int e = 0; e < VEC; ++e) {
+        const int pos = pa + e;
+        const int cy = pos / w, cx = pos - cy * w;
+        in_q[e] = cx >= qrect.x && cx <= qrect.y && cy >= qrect.z && cy <= qrect.w;
+        any_in |= in_q[e];
       }
-    } else {
+      float *out = out_o + (unsigned)ck * uN + pa;
+      const float *qv = q_val + (long long)o * q_obj_stride + (unsigned)ck * uN + pa;
+      float *oq = out + (unsigned)RMNET_CV * uN;
+      if (VEC == 4) {
+        // q_val passthrough, channels 512..1023: v4e * att16 (literal multiply keeps the sign of zero like the reference)
+        float4 x[kChPerThread];
 #pragma unroll
-      for (int k = 0; k < kChPerThread; ++k) oq[(unsigned)k * (unsigned)N] = __ldg(qv + (unsigned)k * (unsigned)N) * (in_q[0] ? 1.0f : 0.0f);
+        for (int k = 0; k < kChPerThread; ++k) x[k] = __ldg(reinterpret_cast<const float4 *>(qv + (unsigned)k * uN));
+#pragma unroll
+        for (int k = 0; k < kChPerThread; ++k) {
+          x[k].x *= in_q[0] ? 1.0f : 0.0f; x[k].y *= in_q[1 % VEC] ? 1.0f : 0.0f;
+          x[k].z *= in_q[2 % VEC] ? 1.0f : 0.0f; x[k].w *= in_q[3 % VEC] ? 1.0f : 0.0f;
+          *reinterpret_cast<float4 *>(oq + (unsigned)k * uN) = x[k];
+        }
+        if (!any_in) {
+#pragma unroll
+          for (int k = 0; k < kChPerThread; ++k) {
+            const float u = s_uniform[cl * kChPerThread + k];
+            *reinterpret_cast<float4 *>(out + (unsigned)k * uN) = make_float4(u, u, u, u);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < kChPerThread; ++k) {
+            const float u = s_uniform[cl * kChPerThread + k];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) if (!in_q[e]) out[(unsigned)k * uN + e] = u;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kChPerThread; ++k) {
+          oq[(unsigned)k * uN] = __ldg(qv + (unsigned)k * uN) * (in_q[0] ? 1.0f : 0.0f);
+          if (!in_q[0]) out[(unsigned)k * uN] = s_uniform[cl * kChPerThread + k];
+        }
+      }
     }
   }
 
-  float res[VEC][kChPerThread];
+  // ------------------------------ phase B: gather the in-region cells ------------------------------
+  const int pos = blockIdx.x * 128 + tid;
+  if (pos >= N) return;
+  const int cy = pos / w, cx = pos - cy * w;
+  if (!(cx >= qrect.x && cx <= qrect.y && cy >= qrect.z && cy <= qrect.w)) return;
+  const int n = (cy - qrect.z) * rw + (cx - qrect.x);  // compact query index
+  const int half = c0 / (RMNET_CV / 2);
+  if (sched_ns) n_splits = __ldg(sched_ns + o);  // KV chunks the persistent tcgen05 kernel used for this object
+  const unsigned ml_stride = (unsigned)n_obj * 2u * (unsigned)nq_pad;        // float2 units between splits
+  const unsigned op_stride = (unsigned)n_obj * RMNET_CV * (unsigned)nq_pad;  // floats between splits
+  const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad + n;
+  float wgt[READ_MAX_SPLITS];
+  float2 st[READ_MAX_SPLITS];
 #pragma unroll
-  for (int e = 0; e < VEC; ++e)
+  for (int s = 0; s < READ_MAX_SPLITS; ++s) st[s] = (s < n_splits) ? __ldg(mlp + (unsigned)s * ml_stride) : make_float2(-INFINITY, 0.f);
+  float m_star = Z > 0 ? 0.f : -INFINITY;
 #pragma unroll
-    for (int k = 0; k < kChPerThread; ++k) res[e][k] = s_uniform[cl * kChPerThread + k];
-
-  if (any_in) {
-    const int half = c0 / (RMNET_CV / 2);
-    if (sched_ns) n_splits = __ldg(sched_ns + o);  // KV chunks the persistent tcgen05 kernel used for this object
-    const unsigned ml_stride = (unsigned)n_obj * 2u * (unsigned)nq_pad;            // float2 units between splits
-    const unsigned op_stride = (unsigned)n_obj * RMNET_CV * (unsigned)nq_pad;      // floats between splits
-    const float2 *mlb = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad;
-    const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)ck) * (unsigned)nq_pad;
+  for (int s = 0; s < READ_MAX_SPLITS; ++s) m_star = fmaxf(m_star, st[s].x);
+  float L = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
 #pragma unroll
-    for (int e = 0; e < VEC; ++e) {
-      if (!in_q[e]) continue;
-      const int n = nidx[e];
-      float m_star = Z > 0 ? 0.f : -INFINITY;
-      for (int s = 0; s < n_splits; ++s) m_star = fmaxf(m_star, __ldg(mlb + (unsigned)s * ml_stride + n).x);
-      float L = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
-      float num[kChPerThread];
-#pragma unroll
-      for (int k = 0; k < kChPerThread; ++k) num[k] = 0.f;
-      for (int s = 0; s < n_splits; ++s) {
-        const float2 st = __ldg(mlb + (unsigned)s * ml_stride + n);
-        if (st.x == -INFINITY) continue;  // a split that saw no cells left its numerators unwritten
-        const float wgt = ex2f(st.x - m_star);
-        L = fmaf(st.y, wgt, L);
-        const float *p = opb + (unsigned)s * op_stride + n;
-        float v[kChPerThread];
-#pragma unroll
-        for (int k = 0; k < kChPerThread; ++k) v[k] = __ldg(p + (unsigned)k * (unsigned)nq_pad);
-#pragma unroll
-        for (int k = 0; k < kChPerThread; ++k) num[k] = fmaf(v[k], wgt, num[k]);
-      }
-      const float inv_l = 1.0f / L;
-#pragma unroll
-      for (int k = 0; k < kChPerThread; ++k) res[e][k] = num[k] * inv_l;
-    }
+  for (int s = 0; s < READ_MAX_SPLITS; ++s) {
+    wgt[s] = (st[s].x == -INFINITY) ? 0.f : ex2f(st[s].x - m_star);  // a split that saw no cells left its numerators unwritten
+    L = fmaf(st[s].y, wgt[s], L);
   }
-  if (VEC == 4) {
+  const float inv_l = 1.0f / L;
+  const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)c0) * (unsigned)nq_pad + n;
+  float *outp = out_o + (unsigned)c0 * uN + pos;
+#pragma unroll 1
+  for (int g = 0; g < kChPerCta; g += 8) {
+    float num[8];
 #pragma unroll
-    for (int k = 0; k < kChPerThread; ++k)
-      *reinterpret_cast<float4 *>(out + (unsigned)k * (unsigned)N) = make_float4(res[0][k], res[1 % VEC][k], res[2 % VEC][k], res[3 % VEC][k]);
-  } else {
+    for (int k = 0; k < 8; ++k) num[k] = 0.f;
 #pragma unroll
-    for (int k = 0; k < kChPerThread; ++k) out[(unsigned)k * (unsigned)N] = res[0][k];
+    for (int s = 0; s < READ_MAX_SPLITS; s += 2) {
+      if (s >= n_splits) break;
+      float v0[8], v1[8];
+      const float *q0 = opb + (unsigned)s * op_stride + (unsigned)g * (unsigned)nq_pad, *q1 = q0 + op_stride;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        v0[k] = (wgt[s] != 0.f) ? __ldg(q0 + (unsigned)k * (unsigned)nq_pad) : 0.f;
+        v1[k] = (wgt[s + 1] != 0.f) ? __ldg(q1 + (unsigned)k * (unsigned)nq_pad) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) num[k] = fmaf(v1[k], wgt[s + 1], fmaf(v0[k], wgt[s], num[k]));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) outp[(unsigned)(g + k) * uN] = num[k] * inv_l;
   }
 }
 
@@ -146,7 +171,7 @@ int launch_merge(const BankView &bank, const float *q_val, long long q_obj_strid
     merge_kernel<4><<<grid, kMergeThreads, 0, st>>>(bank, q_val, q_obj_stride, q_rects, h, w, n_obj, n_splits, ns, W.opart, W.ml,
                                                     W.nq_pad, mem_val);
   } else {
-    dim3 grid(cdiv(N, 32), RMNET_CV / kChPerCta, n_obj);
+    dim3 grid(cdiv(N, 128), RMNET_CV / kChPerCta, n_obj);
     merge_kernel<1><<<grid, kMergeThreads, 0, st>>>(bank, q_val, q_obj_stride, q_rects, h, w, n_obj, n_splits, ns, W.opart, W.ml,
                                                     W.nq_pad, mem_val);
   }
