@@ -136,26 +136,29 @@ merge_kernel(BankView bank, const float *__restrict__ q_val, long long q_obj_str
   const float inv_l = 1.0f / L;
   const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)c0) * (unsigned)nq_pad + n;
   float *outp = out_o + (unsigned)c0 * uN + pos;
+  // 16 channels x 4 splits = 64 independent loads in flight per round trip
 #pragma unroll 1
-  for (int g = 0; g < kChPerCta; g += 8) {
-    float num[8];
+  for (int g = 0; g < kChPerCta; g += 16) {
+    float num[16];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) num[k] = 0.f;
+    for (int k = 0; k < 16; ++k) num[k] = 0.f;
 #pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; s += 2) {
-      if (s >= n_splits) break;
-      float v0[8], v1[8];
-      const float *q0 = opb + (unsigned)s * op_stride + (unsigned)g * (unsigned)nq_pad, *q1 = q0 + op_stride;
+    for (int s0 = 0; s0 < READ_MAX_SPLITS; s0 += 4) {
+      if (s0 >= n_splits) break;
+      float v[4][16];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        v0[k] = (wgt[s] != 0.f) ? __ldg(q0 + (unsigned)k * (unsigned)nq_pad) : 0.f;
-        v1[k] = (wgt[s + 1] != 0.f) ? __ldg(q1 + (unsigned)k * (unsigned)nq_pad) : 0.f;
+      for (int u = 0; u < 4; ++u) {
+        const float *q = opb + (unsigned)(s0 + u) * op_stride + (unsigned)g * (unsigned)nq_pad;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[u][k] = (wgt[s0 + u] != 0.f) ? __ldg(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) num[k] = fmaf(v1[k], wgt[s + 1], fmaf(v0[k], wgt[s], num[k]));
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < 16; ++k) num[k] = fmaf(v[u][k], wgt[s0 + u], num[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) outp[(unsigned)(g + k) * uN] = num[k] * inv_l;
+    for (int k = 0; k < 16; ++k) outp[(unsigned)(g + k) * uN] = num[k] * inv_l;
   }
 }
 
