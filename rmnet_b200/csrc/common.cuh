@@ -209,24 +209,37 @@ __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict
     max_nt = max(max_nt, __reduce_max_sync(0xffffffffu, nqt > 0 ? nt : 0));
   }
   __syncwarp();
-  // candidate k (lane): c = ceil(max_nt / k)
-  const int k = lane + 1;
-  int c = max_nt > 0 ? (max_nt + k - 1) / k : 1;
-  long long cost = 0x7fffffffffffffffLL;
-  if (k <= READ_MAX_SPLITS && (c <= MAX_TILES_PER_SPLIT || k == READ_MAX_SPLITS)) {
-    long long items = 0;
-    for (int o = 0; o < n_obj; ++o) {
-      const int nt = T.nt[o];
-      if (nt > 0 && T.nqt[o] > 0) items += (long long)((nt + c - 1) / c) * 2 * T.nqt[o];
-    }
-    const long long rounds = (items + G - 1) / G;
-    cost = rounds * (long long)(c + 6) * 64 + k;  // +6: per-item prologue/epilogue in tile units; ties -> fewer chunks
-  }
-  long long best = cost;
+  // candidates: every chunk length c in [c_min, 64] (two per lane), c_min from the partial-slot bound
+  const int c_min = max(1, (max_nt + READ_MAX_SPLITS - 1) / READ_MAX_SPLITS);
+  long long best = 0x7fffffffffffffffLL;
+  int best_c = max(c_min, 1);
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, d));
-  const unsigned who = __ballot_sync(0xffffffffu, cost == best);
-  c = __shfl_sync(0xffffffffu, c, __ffs(who) - 1);
+  for (int rep = 0; rep < 2; ++rep) {
+    const int c = lane + 1 + 32 * rep;
+    long long cost = 0x7fffffffffffffffLL;
+    if (c >= c_min && (c <= MAX_TILES_PER_SPLIT) && c <= max(max_nt, 1)) {
+      long long items = 0;
+      int longest = 0;
+      for (int o = 0; o < n_obj; ++o) {
+        const int nt = T.nt[o];
+        if (nt > 0 && T.nqt[o] > 0) {
+          const int ns = (nt + c - 1) / c;
+          items += (long long)ns * 2 * T.nqt[o];
+          longest = max(longest, (nt + ns - 1) / ns);  // balanced chunks: the longest actual chunk
+        }
+      }
+      const long long rounds = (items + G - 1) / G;
+      // makespan estimate in tile units: rounds x (longest chunk + per-item prologue/epilogue ~ 5 tiles); ties -> fewer chunks
+      cost = (rounds * (long long)(longest + 5)) * 128 + (64 - c);
+    }
+    if (cost < best) { best = cost; best_c = c; }
+  }
+  long long bcast = best;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) bcast = min(bcast, __shfl_xor_sync(0xffffffffu, bcast, d));
+  const unsigned who = __ballot_sync(0xffffffffu, best == bcast);
+  int c = __shfl_sync(0xffffffffu, best_c, __ffs(who) - 1);
+  if (max_nt > MAX_TILES_PER_SPLIT * READ_MAX_SPLITS) c = c_min;  // huge banks: the slot bound wins over the chain bound
   if (lane == 0) {
     int acc = 0;
     for (int o = 0; o < n_obj; ++o) {
