@@ -204,17 +204,15 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
   __shared__ SchedTable sched;
 
+  long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 16 : nullptr;  // dev hook
+  if (tstamp && threadIdx.x == 128) tstamp[0] = clock64();
   const int N = h * w;
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
-  __syncthreads();
-  if (blockIdx.x == 0 && threadIdx.x < n_obj) sched_out[threadIdx.x] = sched.ns[threadIdx.x];  // for merge.cu
-  if ((int)blockIdx.x >= sched.ibase[n_obj]) return;  // uniform per CTA, before any barrier / TMEM allocation
-
-  // ---- one-time setup
+  // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1)
+  if (warp == 3) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
     for (int i = 0; i < KST; ++i) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
@@ -234,9 +232,15 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (blockIdx.x == 0 && threadIdx.x < n_obj) sched_out[threadIdx.x] = sched.ns[threadIdx.x];  // for merge.cu
+  if ((int)blockIdx.x >= sched.ibase[n_obj]) {  // no work for this CTA (uniform): give the TMEM back and leave
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(bars->tmem_base), "r"(512u) : "memory");
+    return;
+  }
   const uint32_t tmem = bars->tmem_base;
   PieceIter iter(&sched, n_obj, (int)blockIdx.x, (int)gridDim.x);
   Piece pc;
+  if (tstamp && threadIdx.x == 128) tstamp[1] = clock64();
 
   if (warp == 0) {
     // ================= key-tile TMA producer =================
@@ -347,40 +351,40 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
     int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
     bool first_piece = true;
-    while (iter.next(pc)) {
+    float xq[RMNET_CK];  // this row's 128 query-key channels, fetched one item ahead (overlaps the previous epilogue)
+    auto fetch_q = [&](const Piece &p) {
+      const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + p.o) : make_int4(0, w - 1, 0, h - 1);
+      const int nn = p.qtile * QT + row;
+      const bool live = nn < rect_cells(qr);
+      const float *qp = q_key + (long long)p.o * q_obj_stride + (live ? rect_pos(qr, nn, w) : 0);
+#pragma unroll
+      for (int j = 0; j < RMNET_CK; ++j) xq[j] = live ? __ldg(qp + (long long)j * N) : 0.f;
+    };
+    Piece nxt;
+    bool have = iter.next(pc);
+    if (have) fetch_q(pc);
+    while (have) {
       const int o = pc.o;
-      const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-      const int nq = rect_cells(qrect);
       const int n = pc.qtile * QT + row;
       const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
 
       // ---- Q rows -> 16-bit hi/lo planes in TMEM (A operand of the score product).  All score MMAs of the previous
       //      piece have retired: its last softmax pass waited on their commit.
-      {
-        const bool live = n < nq;
-        const float *qp = q_key + (long long)o * q_obj_stride + (live ? rect_pos(qrect, n, w) : 0);
-#pragma unroll 1
-        for (int c0 = 0; c0 < RMNET_CK; c0 += 64) {  // 64 strided loads in flight per thread per pass
-          float xq[64];
 #pragma unroll
-          for (int j = 0; j < 64; ++j) xq[j] = live ? __ldg(qp + (long long)(c0 + j) * N) : 0.f;
-          uint32_t hi[32], lo[32];
+      for (int c0 = 0; c0 < RMNET_CK; c0 += 32) {
+        uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            lo[j] = 0;
-            split_pack2<FMT, USE_LO>(xq[2 * j], xq[2 * j + 1], hi[j], lo[j]);
-          }
-          TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
-          TMEM_ST16(t_base + TM_Q_HI + c0 / 2 + 16, hi, 16);
-          if (USE_LO) {
-            TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
-            TMEM_ST16(t_base + TM_Q_LO + c0 / 2 + 16, lo, 16);
-          }
+        for (int j = 0; j < 16; ++j) {
+          lo[j] = 0;
+          split_pack2<FMT, USE_LO>(xq[c0 + 2 * j], xq[c0 + 2 * j + 1], hi[j], lo[j]);
         }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(smem_u32(&bars->q_ready));
+        TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
+        if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
       }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(smem_u32(&bars->q_ready));
+      if (tstamp && first_piece && row == 0) tstamp[2] = clock64();
 
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int it = 0; it < pc.n_it; ++it, ++gt) {
@@ -394,6 +398,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         TMEM_LD16(s_addr + 32, sr, 32);
         TMEM_LD16(s_addr + 48, sr, 48);
         tc_wait_ld();
+        if (tstamp && first_piece && it == 0 && row == 0) tstamp[3] = clock64();
         if (dbg && first_piece && it == 0 && blockIdx.x == 0) {
 #pragma unroll
           for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
@@ -463,8 +468,12 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)pc.slot * n_obj + o) * 2 + pc.half) * nq_pad + n;
         *dst = make_float2(m_ref, l_sum);
       }
+      if (tstamp && first_piece && row == 0) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
+      have = iter.next(nxt);
+      if (have) fetch_q(nxt);  // global loads of the next item's Q fly while O is drained below
       mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
       tc_fence_after();
+      if (tstamp && first_piece && row == 0) tstamp[5] = clock64();
       float *ob = opart + (((size_t)pc.slot * n_obj + o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
 #pragma unroll 1
       for (int c = 0; c < CVH; c += 32) {
@@ -476,7 +485,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         for (int j = 0; j < 32; ++j) ob[(size_t)(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
       }
       if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
+      if (tstamp && first_piece && row == 0) tstamp[6] = clock64();
       first_piece = false;
+      pc = nxt;
     }
   }
 

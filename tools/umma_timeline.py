@@ -1,0 +1,35 @@
+"""Dev aid: per-CTA phase timestamps of the tcgen05 kernel (first item of every CTA)."""
+import ctypes, os, sys, numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import bench, rmnet_b200
+L = rmnet_b200.lib()
+L.rmnet_debug_set_umma_dump.argtypes = [ctypes.c_void_p]; L.rmnet_debug_set_umma_dump.restype = None
+dev = torch.device("cuda:0")
+for wlname in ("c2", "c3"):
+    wl = bench.WORKLOADS[wlname]; n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
+    pool = bench.make_pool(wl, 1234, 2)
+    rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=dev)
+    D = lambda f: {k: torch.from_numpy(v).to(dev) for k, v in f.items()}
+    for t in range(T - 1):
+        d = D(pool["frames"][t]); rm.memorize(d["k4"], d["v4"], d["mask"][None], commit=True)
+    d = D(pool["frames"][T - 1])
+    for _ in range(3): rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
+    dbg = torch.zeros(8448 + 148 * 32 + 64, device=dev)
+    torch.cuda.synchronize()
+    L.rmnet_debug_set_umma_dump(dbg.data_ptr())
+    rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
+    torch.cuda.synchronize()
+    L.rmnet_debug_set_umma_dump(None)
+    ts = dbg[8448:8448 + 148 * 32].view(torch.int64).view(148, 16).cpu().numpy()
+    live = ts[:, 6] > 0
+    t = ts[live]
+    rel = (t[:, 1:7] - t[:, :1]).astype(np.float64)
+    names = ["setup(sched,alloc,barriers)", "Q in TMEM", "first S loaded", "last P stored", "last PV retired", "epilogue stored"]
+    print(f"== {wlname}: {live.sum()} CTAs with work; tiles/item median {np.median(t[:,7])}; cycles from kernel entry (median / max):")
+    prev = 0
+    for i, nm in enumerate(names):
+        print(f"   {nm:30s} {np.median(rel[:, i]):9.0f} {rel[:, i].max():9.0f}   (+{np.median(rel[:, i]) - prev:7.0f})")
+        prev = np.median(rel[:, i])
+    per_tile = (rel[:, 3] - rel[:, 2]) / np.maximum(t[:, 7] - 1, 1)
+    print(f"   steady state cycles per tile (median) {np.median(per_tile):.0f}")
