@@ -189,6 +189,14 @@ struct SchedTable {
   int ns[SCHED_MAX_OBJ];         // KV chunks (= partial slots) of object o
   int ibase[SCHED_MAX_OBJ + 1];  // first item of object o
 };
+// ceil(a / b) for 0 < b, a < 2^20 via one float multiply and a fix-up (a 32-bit integer division costs ~25 instructions)
+__device__ __forceinline__ unsigned ceil_div_small(unsigned a, unsigned b, float rcp_b) {
+  unsigned q = (unsigned)((float)a * rcp_b);
+  q += (q * b < a) ? 1u : 0u;
+  q += (q * b < a) ? 1u : 0u;
+  q -= (q > 0 && (q - 1u) * b >= a) ? 1u : 0u;
+  return q;
+}
 // Called by ONE FULL WARP (all 32 lanes); lane 0 writes the table.  G = number of persistent CTAs.
 __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
                                             int n_obj, int h, int w, int G) {
@@ -209,37 +217,35 @@ __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict
     max_nt = max(max_nt, __reduce_max_sync(0xffffffffu, nqt > 0 ? nt : 0));
   }
   __syncwarp();
-  // candidates: every chunk length c in [c_min, 64] (two per lane), c_min from the partial-slot bound
-  const int c_min = max(1, (max_nt + READ_MAX_SPLITS - 1) / READ_MAX_SPLITS);
-  long long best = 0x7fffffffffffffffLL;
-  int best_c = max(c_min, 1);
+  // candidates: every chunk length c in [c_min, 64] (two per lane), c_min from the partial-slot bound.
+  // 32-bit unsigned arithmetic only: 64-bit integer division is emulated with hundreds of instructions.
+  const unsigned c_min = max(1u, ((unsigned)max_nt + READ_MAX_SPLITS - 1) / READ_MAX_SPLITS);
+  unsigned best = 0xffffffffu, best_c = c_min;
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const int c = lane + 1 + 32 * rep;
-    long long cost = 0x7fffffffffffffffLL;
-    if (c >= c_min && (c <= MAX_TILES_PER_SPLIT) && c <= max(max_nt, 1)) {
-      long long items = 0;
-      int longest = 0;
+    const unsigned c = lane + 1 + 32 * rep;
+    unsigned cost = 0xffffffffu;
+    if (c >= c_min && c <= MAX_TILES_PER_SPLIT && c <= (unsigned)max(max_nt, 1)) {
+      unsigned items = 0, longest = 0;
+      const float rcp_c = 1.0f / (float)c;
       for (int o = 0; o < n_obj; ++o) {
-        const int nt = T.nt[o];
+        const unsigned nt = T.nt[o];
         if (nt > 0 && T.nqt[o] > 0) {
-          const int ns = (nt + c - 1) / c;
-          items += (long long)ns * 2 * T.nqt[o];
-          longest = max(longest, (nt + ns - 1) / ns);  // balanced chunks: the longest actual chunk
+          const unsigned ns = ceil_div_small(nt, c, rcp_c);
+          items += ns * 2u * (unsigned)T.nqt[o];
+          longest = max(longest, ceil_div_small(nt, ns, 1.0f / (float)ns));  // balanced chunks: the longest actual chunk
         }
       }
-      const long long rounds = (items + G - 1) / G;
+      const unsigned rounds = (items + G - 1) / (unsigned)G;
       // makespan estimate in tile units: rounds x (longest chunk + per-item prologue/epilogue ~ 5 tiles); ties -> fewer chunks
-      cost = (rounds * (long long)(longest + 5)) * 128 + (64 - c);
+      cost = (rounds * (longest + 5u)) * 128u + (64u - c);
     }
     if (cost < best) { best = cost; best_c = c; }
   }
-  long long bcast = best;
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) bcast = min(bcast, __shfl_xor_sync(0xffffffffu, bcast, d));
+  const unsigned bcast = __reduce_min_sync(0xffffffffu, best);
   const unsigned who = __ballot_sync(0xffffffffu, best == bcast);
-  int c = __shfl_sync(0xffffffffu, best_c, __ffs(who) - 1);
-  if (max_nt > MAX_TILES_PER_SPLIT * READ_MAX_SPLITS) c = c_min;  // huge banks: the slot bound wins over the chain bound
+  int c = (int)__shfl_sync(0xffffffffu, best_c, __ffs(who) - 1);
+  if (max_nt > MAX_TILES_PER_SPLIT * READ_MAX_SPLITS) c = (int)c_min;  // huge banks: the slot bound wins over the chain bound
   if (lane == 0) {
     int acc = 0;
     for (int o = 0; o < n_obj; ++o) {

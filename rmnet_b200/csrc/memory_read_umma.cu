@@ -176,15 +176,17 @@ struct PieceIter {
     if (item >= T->ibase[n_obj]) return false;
     int o = 0;
     while (T->ibase[o + 1] <= item) ++o;  // objects without work own no items and are skipped
-    int r = item - T->ibase[o];
-    const int nqt = T->nqt[o], nt = T->nt[o], ns = T->ns[o];
+    unsigned r = (unsigned)(item - T->ibase[o]);
+    const unsigned nqt = T->nqt[o], nt = T->nt[o], ns = T->ns[o];
     p.o = o;
-    p.qtile = r % nqt; r /= nqt;
-    p.half = r & 1;
-    const int j = r >> 1;
-    p.slot = j;
-    p.tile_begin = (int)(((long long)j * nt) / ns);           // balanced partition of the nt tiles into ns chunks
-    p.n_it = (int)(((long long)(j + 1) * nt) / ns) - p.tile_begin;
+    const unsigned q = r / nqt;       // 32-bit unsigned divisions only (64-bit ones cost hundreds of instructions)
+    p.qtile = (int)(r - q * nqt);
+    p.half = (int)(q & 1u);
+    const unsigned j = q >> 1;
+    p.slot = (int)j;
+    const unsigned t0 = (j * nt) / ns, t1 = ((j + 1u) * nt) / ns;  // balanced partition of the nt tiles into ns chunks
+    p.tile_begin = (int)t0;
+    p.n_it = (int)(t1 - t0);
     return true;
   }
 };
@@ -212,7 +214,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1)
+  if (tstamp && threadIdx.x == 96) tstamp[8] = clock64();
   if (warp == 3) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
+  if (tstamp && threadIdx.x == 96) tstamp[9] = clock64();
+  if (tstamp && threadIdx.x == 32) tstamp[10] = clock64();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
     for (int i = 0; i < KST; ++i) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
@@ -229,6 +234,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (tstamp && threadIdx.x == 32) tstamp[11] = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -315,32 +321,36 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       mbar_wait(smem_u32(&bars->q_ready), n_piece & 1);  // this piece's Q rows are in TMEM
       tc_fence_after();
       ++n_piece;
-      const int gt_end = gt + pc.n_it;
-      issue_qk();
-      if (gt < gt_end) issue_qk();
-      for (int it = 0; it < pc.n_it; ++it, ++pt) {
-        const int s = pt % VST, b = pt & 1;
-        mbar_wait(smem_u32(&bars->p_full[b]), (pt >> 1) & 1);
-        mbar_wait(smem_u32(&bars->v_full[s]), (pt / VST) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t vb = v_smem + s * V_STAGE_BYTES;
-          const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
+      // software pipeline, one code site per product: QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ... | PV(n-2) | PV(n-1)
+      // QK(s) overwrites the S/P buffer that PV(s-2) just consumed: the tensor pipe executes in issue order.
+#pragma unroll 1
+      for (int st = 0; st < pc.n_it + 2; ++st) {
+        if (st >= 2) {
+          const int it = st - 2;
+          const int s = pt % VST, b = pt & 1;
+          mbar_wait(smem_u32(&bars->p_full[b]), (pt >> 1) & 1);
+          mbar_wait(smem_u32(&bars->v_full[s]), (pt / VST) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t vb = v_smem + s * V_STAGE_BYTES;
+            const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
 #pragma unroll
-          for (int kk = 0; kk < MT / 16; ++kk) {
-            const uint64_t bh = umma_desc_sw128(vb + kk * 32);
-            umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
-            if (use_lo) {
-              const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
-              umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
-              umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+            for (int kk = 0; kk < MT / 16; ++kk) {
+              const uint64_t bh = umma_desc_sw128(vb + kk * 32);
+              umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
+              if (use_lo) {
+                const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
+                umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
+                umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+              }
             }
+            umma_commit(smem_u32(&bars->v_empty[s]));
+            umma_commit(smem_u32(&bars->pv_done[b]));
           }
-          umma_commit(smem_u32(&bars->v_empty[s]));
-          umma_commit(smem_u32(&bars->pv_done[b]));
+          __syncwarp();
+          ++pt;
         }
-        __syncwarp();
-        if (gt < gt_end) issue_qk();  // overwrites the S/P buffer PV(it) just consumed: in-order on the tensor pipe
+        if (st < pc.n_it) issue_qk();
       }
     }
   } else if (warp >= 4) {
@@ -355,14 +365,16 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     auto fetch_q = [&](const Piece &p) {
       const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + p.o) : make_int4(0, w - 1, 0, h - 1);
       const int nn = p.qtile * QT + row;
-      const bool live = nn < rect_cells(qr);
-      const float *qp = q_key + (long long)p.o * q_obj_stride + (live ? rect_pos(qr, nn, w) : 0);
+      // rows past the region's last query read cell 0: finite garbage that no one consumes (rows are independent)
+      const float *qp = q_key + (long long)p.o * q_obj_stride + (nn < rect_cells(qr) ? rect_pos(qr, nn, w) : 0);
 #pragma unroll
-      for (int j = 0; j < RMNET_CK; ++j) xq[j] = live ? __ldg(qp + (long long)j * N) : 0.f;
+      for (int j = 0; j < RMNET_CK; ++j) xq[j] = __ldg(qp + j * N);  // 32-bit offsets: one IMAD.WIDE per load
     };
     Piece nxt;
     bool have = iter.next(pc);
+    if (tstamp && row == 0) tstamp[12] = clock64();
     if (have) fetch_q(pc);
+    if (tstamp && row == 0) tstamp[13] = clock64();
     while (have) {
       const int o = pc.o;
       const int n = pc.qtile * QT + row;
@@ -381,6 +393,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
         if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
       }
+      if (tstamp && first_piece && row == 0) tstamp[14] = clock64();
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(smem_u32(&bars->q_ready));
@@ -482,7 +495,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
         tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) ob[(size_t)(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
+        for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
       }
       if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
       if (tstamp && first_piece && row == 0) tstamp[6] = clock64();

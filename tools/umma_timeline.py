@@ -31,5 +31,8 @@ for wlname in ("c2", "c3"):
     for i, nm in enumerate(names):
         print(f"   {nm:30s} {np.median(rel[:, i]):9.0f} {rel[:, i].max():9.0f}   (+{np.median(rel[:, i]) - prev:7.0f})")
         prev = np.median(rel[:, i])
+    ex = (t[:, 8:15] - t[:, :1]).astype(np.float64)
+    for i, nm in enumerate(["sched begin", "sched end", "alloc begin", "alloc end", "iter.next done", "Q loads issued", "Q converted+stored (before wait::st)"]):
+        print(f"      .. {nm:38s} {np.median(ex[:, i]):9.0f}")
     per_tile = (rel[:, 3] - rel[:, 2]) / np.maximum(t[:, 7] - 1, 1)
     print(f"   steady state cycles per tile (median) {np.median(per_tile):.0f}")
