@@ -175,6 +175,26 @@ class ClockSampler:
                 "samples": len(rows)}
 
 
+def shard_clips(n_clips, rank, world):
+    """Clip-parallel sharding: clip i runs on rank i % world; no data-path collective."""
+    return [i for i in range(n_clips) if i % world == rank]
+
+
+def reduce_over_ranks(dev_ms, e2e_s, checksum, device, rank, world):
+    """Timing = MAX over ranks (all_reduce), results = one gather of per-rank checksums to rank 0.
+    Works with NCCL (device = cuda) and with gloo (device = cpu, used by the CPU tests)."""
+    if world == 1:
+        return dev_ms, e2e_s, [checksum]
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([dev_ms, e2e_s], device=device, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    mine = torch.tensor([checksum], device=device, dtype=torch.float64)
+    sums = [torch.zeros(1, device=device, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, sums, dst=0)
+    return float(t[0]), float(t[1]), ([float(x) for x in sums] if rank == 0 else None)
+
+
 def algorithmic_work(counts_m, counts_q, N):
     """SURVEY 8d / BASELINE.md 4: per object  flops = 1280 * M_r * N_r,  bytes = 4*[640*(M_r+N_r) + 1024*N]."""
     flops = sum(1280.0 * m * q for m, q in zip(counts_m, counts_q))
@@ -340,12 +360,7 @@ def run_gpu(args, wl, rank, world, local_rank):
 
     # ---- max over ranks, trivial NCCL gather of a result checksum (north_star: "NCCL only for the result gather")
     checksum = float(m4.double().sum().item())
-    if world > 1:
-        t = torch.tensor([dev_ms, e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s = float(t[0]), float(t[1])
-        sums = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)] if rank == 0 else None
-        dist.gather(torch.tensor([checksum], device=dev, dtype=torch.float64), sums, dst=0)
+    dev_ms, e2e_s, sums = reduce_over_ranks(dev_ms, e2e_s, checksum, dev, rank, world)
     if rank != 0:
         return None
     fps = world * args.steps / (dev_ms * 1e-3)
@@ -359,7 +374,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed", "pool_frames": POOL,
                    "e2e_mode": "pinned host inputs -> H2D -> RegionalMemory.step -> D2H of mem_val every step; copies double-buffered on side streams"},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "roofline": roof, "clocks": clk, "result_checksum": checksum,
+        "gpu_launches": launches, "roofline": roof, "clocks": clk, "result_checksums": sums,
     }
     return line, pool
 
