@@ -120,6 +120,11 @@ class CpuClip:
 
 
 def time_cpu(wl, pool, steps, warmup):
+    try:   # all host threads for the BLAS-backed reader (torchrun exports OMP_NUM_THREADS=1 to its workers)
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     clip = CpuClip(wl, pool)
     for i in range(warmup):
         clip.step(i)

@@ -330,29 +330,42 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
   const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
   const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
   const bool p_nw = xin0 && yin0, p_ne = xin1 && yin0, p_sw = xin0 && yin1, p_se = xin1 && yin1;
-  const long long o_nw = (long long)t.y0 * W + t.x0;
+  // 32-bit in-plane offsets; an out-of-bounds tap reads the thread's own pixel instead and is then replaced by 0
+  // (selected, not multiplied: a NaN there must not leak), so the loop body has no address predication.
+  const int o_self = (int)jj;
+  const int o_nw = t.y0 * W + t.x0;
+  const int a_nw = p_nw ? o_nw : o_self, a_ne = p_ne ? o_nw + 1 : o_self;
+  const int a_sw = p_sw ? o_nw + W : o_self, a_se = p_se ? o_nw + W + 1 : o_self;
+  const float *plane = prev_mask + ((long long)b * K + 1) * n_pixels;  // channel 1; advanced by n_pixels per channel
 
   for (int i0 = 1; i0 < K; i0 += kChunkCh) {
+    const int nch = min(kChunkCh, K - i0);  // warp-uniform
     float v_nw[kChunkCh], v_ne[kChunkCh], v_sw[kChunkCh], v_se[kChunkCh], v_d[kChunkCh];
+    {
+      const float *pl = plane;
 #pragma unroll
-    for (int u = 0; u < kChunkCh; ++u) {
-      const int i = min(i0 + u, K - 1);
-      const float *plane = prev_mask + ((long long)b * K + i) * n_pixels;
-      v_nw[u] = p_nw ? __ldg(plane + o_nw) : 0.f;
-      v_ne[u] = p_ne ? __ldg(plane + o_nw + 1) : 0.f;
-      v_sw[u] = p_sw ? __ldg(plane + o_nw + W) : 0.f;
-      v_se[u] = p_se ? __ldg(plane + o_nw + W + 1) : 0.f;
-      if (DIRECT) v_d[u] = __ldg(plane + jj);
+      for (int u = 0; u < kChunkCh; ++u) {
+        if (u < nch) {
+          v_nw[u] = __ldg(pl + a_nw);
+          v_ne[u] = __ldg(pl + a_ne);
+          v_sw[u] = __ldg(pl + a_sw);
+          v_se[u] = __ldg(pl + a_se);
+          if (DIRECT) v_d[u] = __ldg(pl + o_self);
+          pl += n_pixels;
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < kChunkCh; ++u) {
+      if (u >= nch) break;  // warp-uniform
       const int i = i0 + u;
-      if (i >= K) break;  // warp-uniform
       // same FMA chain as sample_tap (an out-of-bounds tap contributes fma(0, w, acc) = acc exactly)
+      const float x_nw = p_nw ? v_nw[u] : 0.f, x_ne = p_ne ? v_ne[u] : 0.f;
+      const float x_sw = p_sw ? v_sw[u] : 0.f, x_se = p_se ? v_se[u] : 0.f;
       float acc;
-      if (ORDER == 1) acc = __fmaf_rn(v_ne[u], t.ne, __fmul_rn(v_nw[u], t.nw));
-      else acc = __fmaf_rn(v_nw[u], t.nw, __fmul_rn(v_ne[u], t.ne));
-      acc = __fmaf_rn(v_se[u], t.se, __fmaf_rn(v_sw[u], t.sw, acc));
+      if (ORDER == 1) acc = __fmaf_rn(x_ne, t.ne, __fmul_rn(x_nw, t.nw));
+      else acc = __fmaf_rn(x_nw, t.nw, __fmul_rn(x_ne, t.ne));
+      acc = __fmaf_rn(x_se, t.se, __fmaf_rn(x_sw, t.sw, acc));
       const bool hit_w = live && (__fmul_rn(acc, t.valid) >= thr);
       warp_box_to_smem(s_acc + i * 5, __ballot_sync(0xffffffffu, hit_w), one_row, x_lane0, y_lane0, hit_w, x, y, lane);
       if (DIRECT) {
@@ -360,6 +373,7 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
         warp_box_to_smem(s_acc + (K + i) * 5, __ballot_sync(0xffffffffu, hit_d), one_row, x_lane0, y_lane0, hit_d, x, y, lane);
       }
     }
+    plane += (long long)kChunkCh * n_pixels;
   }
   __syncthreads();
   // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it
