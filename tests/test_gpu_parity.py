@@ -384,6 +384,59 @@ def test_regional_path_vs_oracle_with_temp_and_commit(impl_name, impl, cfg):
     assert (st[:n, 6] == 0).all()   # no overflow
 
 
+@pytest.mark.parametrize("fmt_name,fmt", [("bf16", rmnet_b200.ELEM_BF16), ("fp16", rmnet_b200.ELEM_FP16)])
+@pytest.mark.parametrize("prec_name,prec,tol", [("split3", rmnet_b200.RMNET_PREC_SPLIT3, TOL_STRICT), ("single", rmnet_b200.RMNET_PREC_SINGLE, TOL_FAST)])
+def test_umma_formats_and_precisions(fmt_name, fmt, prec_name, prec, tol):
+    """Both 16-bit plane formats (instruction-descriptor bit) and both precision modes of the tcgen05 kernel."""
+    if not _impl_available(rmnet_b200.RMNET_IMPL_UMMA):
+        pytest.skip("tcgen05 kernel not built")
+    n, T, h, w = 2, 3, 15, 27
+    ins = synth.memory_read_inputs(91, n, T, h, w, 0.5)
+    ref = oracle.memory_read(*ins, dtype=np.float64)[0]
+    got = ops.memory_reader_forward(*(cu(x) for x in ins), precision=prec, impl=rmnet_b200.RMNET_IMPL_UMMA, elem_format=fmt).cpu().numpy()
+    err = np.abs(got[:, :synth.CV] - ref[:, :synth.CV]).max()
+    print(f"[{fmt_name}/{prec_name}] max-abs {err:.3e}")
+    assert err <= tol
+    np.testing.assert_array_equal(got[:, synth.CV:], ins[3])
+
+
+@pytest.mark.parametrize("impl_name,impl", IMPLS, ids=[i[0] for i in IMPLS])
+def test_regional_edge_cases_absent_and_tiny_objects(impl_name, impl):
+    """Objects the reference treats specially: an absent object (no pixel >= 0.5 -> full-frame box, dense memory and
+    query), a tiny object (< 10 pixels -> full frame too), an object whose warped mask leaves the frame, and an object
+    hugging the border (loosened box clamps).  reg_att_map_generator.cu:57-74."""
+    if not _impl_available(impl):
+        pytest.skip("tcgen05 kernel not built")
+    n, T, H, W = 4, 2, 96, 150
+    K = n + 1
+    rng = np.random.default_rng(101)
+    lw, uw, lh, uh = oracle.pad_amounts(H, W)
+    h, w = (H + lh + uh) // 16, (W + lw + uw) // 16
+    mk, mv, qk, qv = synth.memory_read_inputs(102, n, T, h, w, 0.5)
+    masks = np.zeros((T, K, H, W), np.float32)
+    masks[:, 0] = 1.0
+    for t in range(T):
+        masks[t, 2, 40:43, 60:63] = 1.0            # 9 pixels: below n_pts_threshold -> full frame
+        masks[t, 3, 0:20, 0:30] = 1.0              # hugging the top-left corner
+        masks[t, 4, 70:96, 120:150] = 0.75         # bottom-right corner
+    flow = np.zeros((2, H, W), np.float32)
+    flow[0] = 400.0                                # warps every sample out of the frame -> nothing >= 0.5 -> full frame
+    rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV, impl=impl)
+    for t in range(T):
+        bb = rm.memorize(cu(mk[:, :, t]), cu(mv[:, :, t]), cu(masks[t][None]), commit=True)
+        np.testing.assert_array_equal(bb.cpu().numpy(), oracle.reg_att_map(oracle.pad_divide_by(masks[t])[0][None])[1])
+    for fl in (flow, np.zeros_like(flow)):
+        m4, cur_bb = rm.read(cu(qk[0]), cu(qv[0]), cu(masks[-1][None]), cu(fl[None]))
+        att_m = np.stack([oracle.reg_att_map(oracle.pad_divide_by(masks[t])[0][None])[0][0, 1:] for t in range(T)], 1)
+        att_q, bb_q = oracle.get_att_map(masks[-1][None], fl[None], arith="cuda")
+        att_qp, _ = oracle.pad_divide_by(att_q[0, 1:])
+        ref = oracle.regional_memory_read(mk, mv, att_m, qk[0], qv[0], att_qp, dtype=np.float64)
+        np.testing.assert_array_equal(cur_bb.cpu().numpy(), bb_q)
+        got = m4.cpu().numpy()
+        assert np.abs(got[:, :synth.CV] - ref[:, :synth.CV]).max() <= TOL_STRICT
+        np.testing.assert_array_equal(got[:, synth.CV:], ref[:, synth.CV:])
+
+
 def test_step_equals_memorize_then_read():
     """RegionalMemory.step (one pass over prev_mask for both sides) == memorize() + read() on the same inputs; the
     same est_masks[t-1] feeds both sides in the reference loop (models/rmnet.py:412-414, :431)."""
