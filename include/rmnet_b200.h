@@ -113,11 +113,15 @@ RMNET_API int rmnet_warp_att_map_forward(const float *prev_mask, const float *fl
  *   flow != NULL, bbox_in_padded_frame = 0 : the segment side, :431 (warp + box in raw coordinates) + :307 + :356.
  *   pad_* = pad_divide_by amounts (lw, uw, lh, uh); bboxes [B,K,4]; cell_rects [B,K,4] (cx0,cx1,cy0,cy1), channel 0
  *   and empty boxes -> (0,-1,0,-1); workspace as rmnet_reg_att_map_forward.
+ *   k_scan: 0 or K = scan every channel like the reference.  2 <= k_scan < K = read only channels [1, k_scan) and report
+ *   channels >= k_scan as ABSENT objects (what the reference computes for an all-below-threshold channel).  Valid when
+ *   those channels are known to stay below prob_threshold -- the reference's frame loop guarantees it for
+ *   j > n_max_objects (their logit is forced to -16.1181, models/rmnet.py:444-448).
  * ------------------------------------------------------------------------------------------- */
 RMNET_API int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, int K, int H, int W,
                                            int sampler, float prob_threshold, int n_pts_threshold,
                                            int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t, int pad_b,
-                                           int bbox_in_padded_frame, int *bboxes, int *cell_rects,
+                                           int bbox_in_padded_frame, int k_scan, int *bboxes, int *cell_rects,
                                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* Both sides of one frame in ONE pass over prev_mask (the memorise side and the segment side read the same
@@ -126,7 +130,7 @@ RMNET_API int rmnet_regional_boxes_forward(const float *mask, const float *flow,
 RMNET_API int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W,
                                           int sampler, float prob_threshold, int n_pts_threshold,
                                           int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t, int pad_b,
-                                          int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
+                                          int k_scan, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
                                           void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -194,7 +198,7 @@ RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_
 RMNET_API int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask,
                                const float *flow, int K, int H, int W, int sampler, float prob_threshold,
                                int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t,
-                               int pad_b, const float *k4, const float *v4, const float *q_key,
+                               int pad_b, int k_scan, const float *k4, const float *v4, const float *q_key,
                                const float *q_val, int n_obj, int elem_format, int precision, int impl,
                                int commit, int *boxes_out, float *mem_val, void *box_workspace,
                                size_t box_workspace_bytes, void *read_workspace, size_t read_workspace_bytes,

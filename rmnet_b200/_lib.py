@@ -35,9 +35,9 @@ PROTOTYPES = {
     "rmnet_warp_att_map_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
                                            c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_regional_boxes_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
-                                             c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                             c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_frame_regions_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_int,
-                                            c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                            c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                             c_void_p]),
     "rmnet_cell_rects_from_bboxes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "rmnet_bank_bytes": (c_size_t, [c_int, c_int]),
@@ -49,7 +49,7 @@ PROTOTYPES = {
     "rmnet_bank_memory_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_frame_step": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
-                                 c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                 c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "rmnet_memory_reader_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_memory_reader_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

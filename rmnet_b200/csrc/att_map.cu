@@ -54,6 +54,7 @@ __device__ __forceinline__ void ws_accumulate(int *ws, const BoxAcc &a) {
 struct BoxFinalize {
   int Hf, Wf, off_x, off_y;  // frame of the bbox
   int n_pts_threshold, loose, force_full;
+  int k_scan;                // channels [1, k_scan) are scanned; channels >= k_scan are reported as absent objects
   int *rects;                // [B,K,4] or nullptr
   int rect_pad_l, rect_pad_t, cell_h, cell_w;
 };
@@ -164,7 +165,11 @@ bbox_scan_kernel(const float *__restrict__ mask, int K, int H, int W, float thr,
     __threadfence();
     finalize_channel(ws_ch, bboxes, (long long)b * K + i, fin);
     atomicExch(ws_ch + 5, 0);
-    if (i == 1) finalize_channel0(bboxes, (long long)b * K, fin);
+    if (i == 1) {
+      finalize_channel0(bboxes, (long long)b * K, fin);
+      for (int u = fin.k_scan; u < K; ++u)  // unscanned channels: their (zero) accumulators give the absent-object box
+        finalize_channel(ws + ((long long)b * 2 * (K + 1) + u) * kWsIntsPerChannel, bboxes, (long long)b * K + u, fin);
+    }
   }
 }
 
@@ -338,8 +343,9 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
   const int a_sw = p_sw ? o_nw + W : o_self, a_se = p_se ? o_nw + W + 1 : o_self;
   const float *plane = prev_mask + ((long long)b * K + 1) * n_pixels;  // channel 1; advanced by n_pixels per channel
 
-  for (int i0 = 1; i0 < K; i0 += kChunkCh) {
-    const int nch = min(kChunkCh, K - i0);  // warp-uniform
+  const int Ks = fin_warp.k_scan;  // channels >= Ks are known to be empty (absent objects): not read at all
+  for (int i0 = 1; i0 < Ks; i0 += kChunkCh) {
+    const int nch = min(kChunkCh, Ks - i0);  // warp-uniform
     float v_nw[kChunkCh], v_ne[kChunkCh], v_sw[kChunkCh], v_se[kChunkCh], v_d[kChunkCh];
     {
       const float *pl = plane;
@@ -463,7 +469,8 @@ size_t rmnet_reg_att_map_workspace_bytes(int B, int K) {
 }
 
 static void make_finalize(BoxFinalize &fin, bool padded, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b, float thr,
-                          int n_pts, int loose, int *rects) {
+                          int n_pts, int loose, int k_scan, int *rects) {
+  fin.k_scan = k_scan;
   fin.Hf = padded ? H + pad_t + pad_b : H;
   fin.Wf = padded ? W + pad_l + pad_r : W;
   fin.off_x = padded ? pad_l : 0;
@@ -485,12 +492,13 @@ static int launch_scan(const float *mask, int B, int K, int H, int W, float thr,
   const bool vec = n_pixels % 4 == 0 && W >= 4 && ((uintptr_t)mask % 16 == 0);
   // ~8 CTAs per SM over all channels: each CTA streams a contiguous chunk (multiple of the 4096-float tile)
   long long want_ctas = 148LL * 8;
-  long long per_channel = (want_ctas + (long long)(K - 1) * B - 1) / ((long long)(K - 1) * B);
+  const int n_scan = fin.k_scan - 1;
+  long long per_channel = (want_ctas + (long long)n_scan * B - 1) / ((long long)n_scan * B);
   if (per_channel < 1) per_channel = 1;
   long long elems = (n_pixels + per_channel - 1) / per_channel;
   elems = (elems + 4095) / 4096 * 4096;
   const int chunks = (int)((n_pixels + elems - 1) / elems);
-  dim3 grid(chunks, K - 1, B);
+  dim3 grid(chunks, n_scan, B);
   if (vec) bbox_scan_kernel<4><<<grid, kThreads, 0, st>>>(mask, K, H, W, thr, fin, (int)elems, bboxes, (int *)workspace);
   else bbox_scan_kernel<1><<<grid, kThreads, 0, st>>>(mask, K, H, W, thr, fin, (int)elems, bboxes, (int *)workspace);
   RMNET_LAUNCH_CHECK();
@@ -525,7 +533,7 @@ int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, flo
   int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, nullptr, 0, 0, 0, 0};
+  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, K, nullptr, 0, 0, 0, 0};
   if ((rc = launch_scan(mask, B, K, H, W, prob_threshold, fin, bboxes, workspace, st))) return rc;
   if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
   return RMNET_OK;
@@ -533,7 +541,7 @@ int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, flo
 
 int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, int K, int H, int W, int sampler,
                                  float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
-                                 int pad_t, int pad_b, int bbox_in_padded_frame, int *bboxes, int *cell_rects,
+                                 int pad_t, int pad_b, int bbox_in_padded_frame, int k_scan, int *bboxes, int *cell_rects,
                                  void *workspace, size_t workspace_bytes, void *stream) {
   int rc = check_common(mask, B, K, H, W, bboxes, workspace, workspace_bytes);
   if (rc) return rc;
@@ -545,8 +553,10 @@ int rmnet_regional_boxes_forward(const float *mask, const float *flow, int B, in
   RMNET_CHECK_ARG(K <= 1024, "K too large");
   cudaStream_t st = (cudaStream_t)stream;
   BoxFinalize fin;
+  if (k_scan <= 0 || k_scan > K) k_scan = K;
+  RMNET_CHECK_ARG(k_scan >= 2, "k_scan must be >= 2");
   make_finalize(fin, bbox_in_padded_frame != 0, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold,
-                n_bbox_loose_pixels, cell_rects);
+                n_bbox_loose_pixels, k_scan, cell_rects);
   if (flow) return launch_warp_scan(mask, flow, B, K, H, W, sampler, prob_threshold, fin, bboxes, workspace, st);
   return launch_scan(mask, B, K, H, W, prob_threshold, fin, bboxes, workspace, st);
 }
@@ -569,7 +579,7 @@ int rmnet_warp_forward(const float *img0, const float *flow, int B, int C, int H
 
 int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
                                 float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
-                                int pad_t, int pad_b, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
+                                int pad_t, int pad_b, int k_scan, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
                                 void *workspace, size_t workspace_bytes, void *stream) {
   int rc = check_common(prev_mask, B, K, H, W, mem_bboxes, workspace, workspace_bytes);
   if (rc) return rc;
@@ -581,8 +591,10 @@ int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B
   RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
   RMNET_CHECK_ARG(K <= 512, "K too large");
   BoxFinalize fw, fd;
-  make_finalize(fw, false, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, cur_rects);
-  make_finalize(fd, true, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, mem_rects);
+  if (k_scan <= 0 || k_scan > K) k_scan = K;
+  RMNET_CHECK_ARG(k_scan >= 2, "k_scan must be >= 2");
+  make_finalize(fw, false, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, k_scan, cur_rects);
+  make_finalize(fd, true, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, k_scan, mem_rects);
   return launch_frame_boxes(prev_mask, flow, B, K, H, W, sampler, prob_threshold, fw, cur_bboxes, &fd, mem_bboxes, workspace,
                             (cudaStream_t)stream);
 }
@@ -596,7 +608,7 @@ int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B,
   RMNET_CHECK_ARG(K <= 1024, "K too large");
   RMNET_CHECK_ARG(sampler == RMNET_SAMPLER_CUDNN || sampler == RMNET_SAMPLER_ATEN, "bad sampler %d", sampler);
   cudaStream_t st = (cudaStream_t)stream;
-  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, nullptr, 0, 0, 0, 0};
+  BoxFinalize fin = {H, W, 0, 0, n_pts_threshold, n_bbox_loose_pixels, 0, K, nullptr, 0, 0, 0, 0};
   if ((rc = launch_warp_scan(prev_mask, flow, B, K, H, W, sampler, prob_threshold, fin, bboxes, workspace, st))) return rc;
   if (att_full) return launch_fill(bboxes, B, K, H, W, att_full, st);
   return RMNET_OK;

@@ -65,7 +65,7 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
 
 int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask, const float *flow,
                      int K, int H, int W, int sampler, float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels,
-                     int pad_l, int pad_r, int pad_t, int pad_b, const float *k4, const float *v4, const float *q_key,
+                     int pad_l, int pad_r, int pad_t, int pad_b, int k_scan, const float *k4, const float *v4, const float *q_key,
                      const float *q_val, int n_obj, int elem_format, int precision, int impl, int commit, int *boxes_out,
                      float *mem_val, void *box_workspace, size_t box_workspace_bytes, void *read_workspace,
                      size_t read_workspace_bytes, void *stream) {
@@ -74,7 +74,7 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   const long long N = (long long)h * w;
   int *mem_bb = boxes_out, *mem_rc = boxes_out + 4 * K, *cur_bb = boxes_out + 8 * K, *cur_rc = boxes_out + 12 * K;
   int rc = rmnet_frame_regions_forward(prev_mask, flow, 1, K, H, W, sampler, prob_threshold, n_pts_threshold,
-                                       n_bbox_loose_pixels, pad_l, pad_r, pad_t, pad_b, mem_bb, mem_rc, cur_bb, cur_rc,
+                                       n_bbox_loose_pixels, pad_l, pad_r, pad_t, pad_b, k_scan, mem_bb, mem_rc, cur_bb, cur_rc,
                                        box_workspace, box_workspace_bytes, stream);
   if (rc) return rc;
   rc = rmnet_bank_memorize(bank, bank_bytes, n_slots, cap_cells, k4, RMNET_CK * N, N, v4, RMNET_CV * N, N, mem_rc + 4, n_obj,

@@ -77,13 +77,17 @@ class RegionalMemory:
     """
 
     def __init__(self, n_objects, frame_hw, max_frames, device, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                 elem_format=ELEM_BF16):
+                 elem_format=ELEM_BF16, scan_all_channels=False):
         H, W = frame_hw
         self.lw, self.uw, self.lh, self.uh = ops.pad_amounts(H, W)
         self.Hp, self.Wp = H + self.lh + self.uh, W + self.lw + self.uw
         self.h, self.w = self.Hp // 16, self.Wp // 16
         self.n = int(n_objects)
         self.precision, self.impl = precision, impl
+        # The reference scans all K-1 mask channels but only ever uses the boxes of objects 1..n (models/rmnet.py:326-331);
+        # channels above n_max_objects are forced to probability ~1e-7 by its frame loop (:444-448), i.e. absent objects.
+        # By default only channels 1..n are read and the rest are reported as absent (identical boxes on such inputs).
+        self.k_scan = 0 if scan_all_channels else self.n + 1
         self.bank = ops.MemoryBank(self.n, self.h, self.w, max_frames, device, elem_format)
         self._boxes = None
 
@@ -91,14 +95,14 @@ class RegionalMemory:
         """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks [1,K,H,W]: the UNPADDED soft
         masks RMNet.memorize receives (the zero padding of :212 is applied analytically).  Returns bboxes [1,K,4] in
         padded coordinates, exactly what the reference's memorize returns (:244, :250)."""
-        bboxes, rects = ops.regional_boxes(masks, None, padded_frame=True)
+        bboxes, rects = ops.regional_boxes(masks, None, padded_frame=True, k_scan=self.k_scan)
         self.bank.memorize(k4, v4, rects[0, 1:self.n + 1], commit)
         return bboxes
 
     def read(self, k4q, v4q, prev_mask, flow, out=None):
         """k4q [128,h,w], v4q [512,h,w]: kv_query outputs of the current frame (:315); prev_mask [1,K,H,W] and
         flow [1,2,H,W] in UNPADDED coordinates (:431).  Returns (m4 [n,1024,h,w], curr_bbox [1,K,4])."""
-        bbox, rects = ops.regional_boxes(prev_mask, flow, padded_frame=False)
+        bbox, rects = ops.regional_boxes(prev_mask, flow, padded_frame=False, k_scan=self.k_scan)
         m4 = self.bank.read(k4q, v4q, rects[0, 1:self.n + 1], self.n, self.precision, self.impl, out=out)
         return m4, bbox
 
@@ -127,7 +131,7 @@ class RegionalMemory:
         ws = ops._zero_ws(dev, 4096)
         ops.check(ops.lib().rmnet_frame_step(
             bank.ptr, bank.nbytes, bank.n_slots, bank.cap, prev_mask.data_ptr(), flow.data_ptr(), K, H, W,
-            ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, k4.data_ptr(), v4.data_ptr(),
+            ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, self.k_scan, k4.data_ptr(), v4.data_ptr(),
             k4q.data_ptr(), v4q.data_ptr(), self.n, bank.elem_format, self.precision, self.impl, 1 if commit else 0,
             self._boxes.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), bank._ws_ptr, bank._ws.numel() - 1024,
             torch.cuda.current_stream(dev).cuda_stream), "frame_step")

@@ -105,7 +105,7 @@ def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10
 
 
 def regional_boxes(mask, flow=None, padded_frame=True, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64,
-                   sampler=None):
+                   sampler=None, k_scan=0):
     """One launch: bounding boxes + /16 cell rectangles from the UNPADDED soft masks [B,K,H,W].
     flow=None, padded_frame=True  <->  pad_divide_by + get_att_map(masks) + interpolate(1/16)   (models/rmnet.py:212, :244-245)
     flow given, padded_frame=False <->  get_att_map(prev_mask, flow) + pad + interpolate(1/16)  (:431, :307, :356)
@@ -125,12 +125,12 @@ def regional_boxes(mask, flow=None, padded_frame=True, prob_threshold=0.5, n_pts
         check(lib().rmnet_regional_boxes_forward(mask.data_ptr(), flow.data_ptr() if flow is not None else None, B, K, H, W,
                                                  default_sampler() if sampler is None else sampler, float(prob_threshold),
                                                  int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh,
-                                                 1 if padded_frame else 0, bboxes.data_ptr(), rects.data_ptr(), ws.data_ptr(),
+                                                 1 if padded_frame else 0, int(k_scan), bboxes.data_ptr(), rects.data_ptr(), ws.data_ptr(),
                                                  ws.numel(), _stream(dev)), "regional_boxes_forward")
     return bboxes, rects
 
 
-def frame_regions(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64, sampler=None):
+def frame_regions(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loose_pixels=64, sampler=None, k_scan=0):
     """Both region descriptors of a frame in one pass over prev_mask [B,K,H,W] (unpadded) and flow [B,2,H,W]:
     -> (mem_bboxes, mem_rects, cur_bboxes, cur_rects), each [B,K,4] int32  (see regional_boxes for the two halves)."""
     _require(prev_mask, "prev_mask")
@@ -145,7 +145,7 @@ def frame_regions(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbo
         ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
         check(lib().rmnet_frame_regions_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
                                                 default_sampler() if sampler is None else sampler, float(prob_threshold),
-                                                int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh,
+                                                int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh, int(k_scan),
                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
                                                 ws.data_ptr(), ws.numel(), _stream(dev)), "frame_regions_forward")
     return out[0], out[1], out[2], out[3]

@@ -437,6 +437,28 @@ def test_regional_edge_cases_absent_and_tiny_objects(impl_name, impl):
         np.testing.assert_array_equal(got[:, synth.CV:], ref[:, synth.CV:])
 
 
+def test_k_scan_reports_unscanned_channels_as_absent_objects():
+    """k_scan = n+1 reads only the channels of real objects; on inputs whose remaining channels are empty (the
+    reference's frame loop forces them to ~1e-7, models/rmnet.py:444-448) every output equals the full scan."""
+    H, W, K, n = 240, 432, 11, 3
+    rng = np.random.default_rng(111)
+    lab = synth.rect_label_map(rng, n, H, W)
+    mask = synth.soft_masks(rng, lab, K, sharp=12.0)[None]        # channels > n: softmax noise, far below 0.5
+    assert mask[0, n + 1:].max() < 0.5
+    flow = synth.flow_field(rng, H, W, 2.0)[None]
+    full = ops.frame_regions(cu(mask), cu(flow))
+    part = ops.frame_regions(cu(mask), cu(flow), k_scan=n + 1)
+    for a, b in zip(full, part):
+        np.testing.assert_array_equal(a.cpu().numpy(), b.cpu().numpy())
+    for padded, fl in ((True, None), (False, flow)):
+        a = ops.regional_boxes(cu(mask), None if fl is None else cu(fl), padded_frame=padded)
+        b = ops.regional_boxes(cu(mask), None if fl is None else cu(fl), padded_frame=padded, k_scan=n + 1)
+        np.testing.assert_array_equal(a[0].cpu().numpy(), b[0].cpu().numpy())
+        np.testing.assert_array_equal(a[1].cpu().numpy(), b[1].cpu().numpy())
+    mp, _ = oracle.pad_divide_by(mask[0])
+    np.testing.assert_array_equal(part[0].cpu().numpy(), oracle.reg_att_map(mp[None])[1])
+
+
 def test_step_equals_memorize_then_read():
     """RegionalMemory.step (one pass over prev_mask for both sides) == memorize() + read() on the same inputs; the
     same est_masks[t-1] feeds both sides in the reference loop (models/rmnet.py:412-414, :431)."""
