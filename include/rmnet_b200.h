@@ -176,12 +176,15 @@ RMNET_API int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells
  *   q_rects [n_obj,4] cell rectangles of the query frame (device); NULL = dense (all cells).
  *   mem_val [n_obj,1024,h,w] f32: channels 0..511 the memory read, 512..1023 the (masked) q_val.
  *   workspace: rmnet_memory_read_workspace_bytes(...) bytes (partial results of the split-KV pass).
- *   stages: RMNET_STAGE_ALL normally; RMNET_STAGE_PARTIAL / RMNET_STAGE_MERGE run only the split-KV
- *     attention kernel / only the merge+scatter kernel (so a benchmark can time each launch alone).
+ *   stages: RMNET_STAGE_ALL normally; RMNET_STAGE_QUERY / _PARTIAL / _MERGE run only the query-side preparation
+ *     (k4e*att16 packed for the tensor cores, v4e*att16 into mem_val[:,512:]) / the split-KV attention kernel / the
+ *     merge+scatter kernel, each of which needs its predecessors' results from an earlier call with the same arguments
+ *     (so a benchmark can time each launch alone).
  * ------------------------------------------------------------------------------------------- */
 #define RMNET_STAGE_PARTIAL 1
 #define RMNET_STAGE_MERGE 2
-#define RMNET_STAGE_ALL 3
+#define RMNET_STAGE_QUERY 4 /* query-side preparation: packed query keys + the q_val passthrough half of mem_val */
+#define RMNET_STAGE_ALL 7
 RMNET_API size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells);
 RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells,
                            const float *q_key, const float *q_val, long long q_obj_stride,
@@ -193,7 +196,8 @@ RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_
  * One frame of the reference's loop body in ONE call (models/rmnet.py:414-432 minus the convolutions), batch 1:
  *   rmnet_frame_regions_forward(prev_mask, flow)  ->  rmnet_bank_memorize(k4, v4, mem_rects[1..n])
  *   ->  rmnet_bank_memory_read(q_key, q_val shared by all objects, cur_rects[1..n])  ->  mem_val [n_obj,1024,h,w]
- *   boxes_out [4][K][4] i32 = mem_bboxes, mem_rects, cur_bboxes, cur_rects.  4 kernels + 1 memset (+1 on commit).
+ *   boxes_out [4][K][4] i32 = mem_bboxes, mem_rects, cur_bboxes, cur_rects.  4 kernels (+1 on commit), chained with
+ *   programmatic dependent launch: regions -> pack (memory + query side) [-> commit] -> tcgen05 read -> merge.
  * ------------------------------------------------------------------------------------------- */
 RMNET_API int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask,
                                const float *flow, int K, int H, int W, int sampler, float prob_threshold,

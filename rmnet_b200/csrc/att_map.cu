@@ -315,10 +315,14 @@ template <int ORDER, bool DIRECT>
 __global__ void __launch_bounds__(kThreads)
 frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
                    float inv_w, float inv_h, float thr, BoxFinalize fin_warp, BoxFinalize fin_direct,
-                   int *__restrict__ bboxes_warp, int *__restrict__ bboxes_direct, int *__restrict__ ws) {
+                   int *__restrict__ bboxes_warp, int *__restrict__ bboxes_direct, int *__restrict__ ws,
+                   float *__restrict__ clear, int n_clear) {
   extern __shared__ int s_acc[];  // [2][K][5] CTA accumulators (zero identity, mins inverted): warped, direct
   __shared__ bool s_last;
+  pdl_trigger();  // head of the frame-step chain: the successor (bank pack) may start launching; it waits for this grid
   const int b = blockIdx.y;
+  // side duty for rmnet_frame_step: zero the bank's temporary-frame value sums (replaces a memset node in the chain)
+  if (clear && blockIdx.x == 0 && b == 0) for (int k = threadIdx.x; k < n_clear; k += kThreads) clear[k] = 0.f;
   const long long n_pixels = (long long)H * W;
   const float *fl = flow + (long long)b * 2 * n_pixels;
   for (int k = threadIdx.x; k < 2 * K * 5; k += kThreads) s_acc[k] = 0;
@@ -382,8 +386,10 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
     plane += (long long)kChunkCh * n_pixels;
   }
   __syncthreads();
-  // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it
+  // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it.  Only the threads that publish
+  // accumulators pay for the fence (a device-wide fence by all 256 threads was 13 % of this kernel's stall samples).
   int *ws_b = ws + (long long)b * 2 * (K + 1) * kWsIntsPerChannel;
+  bool published = false;
   for (int e = threadIdx.x; e < (DIRECT ? 2 : 1) * K; e += kThreads) {
     const int set = e / K, i = e - set * K;
     if (i >= 1 && s_acc[e * 5] > 0) {
@@ -393,9 +399,10 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
       atomicMax(w + 2, s_acc[e * 5 + 2]);
       atomicMax(w + 3, s_acc[e * 5 + 3]);
       atomicMax(w + 4, s_acc[e * 5 + 4]);
+      published = true;
     }
   }
-  __threadfence();
+  if (published) __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     int ticket = atomicAdd(ws_b + K * kWsIntsPerChannel, 1);
@@ -507,7 +514,7 @@ static int launch_scan(const float *mask, int B, int K, int H, int W, float thr,
 
 static int launch_frame_boxes(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler, float thr,
                               const BoxFinalize &fin_warp, int *bboxes_warp, const BoxFinalize *fin_direct, int *bboxes_direct,
-                              void *workspace, cudaStream_t st) {
+                              void *workspace, cudaStream_t st, float *clear = nullptr, int n_clear = 0) {
   const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
   const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
   dim3 grid((unsigned)(((long long)H * W + kThreads - 1) / kThreads), B);
@@ -515,7 +522,7 @@ static int launch_frame_boxes(const float *prev_mask, const float *flow, int B, 
   const BoxFinalize fd = fin_direct ? *fin_direct : fin_warp;
 #define RMNET_LAUNCH_FB(O, D)                                                                                              \
   frame_boxes_kernel<O, D><<<grid, kThreads, smem, st>>>(prev_mask, flow, K, H, W, inv_w, inv_h, thr, fin_warp, fd, bboxes_warp, \
-                                                         bboxes_direct, (int *)workspace)
+                                                         bboxes_direct, (int *)workspace, clear, n_clear)
   if (sampler == RMNET_SAMPLER_CUDNN) { if (fin_direct) RMNET_LAUNCH_FB(0, true); else RMNET_LAUNCH_FB(0, false); }
   else { if (fin_direct) RMNET_LAUNCH_FB(1, true); else RMNET_LAUNCH_FB(1, false); }
 #undef RMNET_LAUNCH_FB
@@ -581,6 +588,18 @@ int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B
                                 float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
                                 int pad_t, int pad_b, int k_scan, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
                                 void *workspace, size_t workspace_bytes, void *stream) {
+  return rmnet::frame_regions_chain_head(prev_mask, flow, B, K, H, W, sampler, prob_threshold, n_pts_threshold, n_bbox_loose_pixels,
+                                         pad_l, pad_r, pad_t, pad_b, k_scan, mem_bboxes, mem_rects, cur_bboxes, cur_rects, workspace,
+                                         workspace_bytes, nullptr, 0, stream);
+}
+}  // extern "C"
+
+// Internal entry (also the head of rmnet_frame_step's PDL chain): `clear[0..n_clear)` is zeroed by the same launch.
+int rmnet::frame_regions_chain_head(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
+                                    float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r,
+                                    int pad_t, int pad_b, int k_scan, int *mem_bboxes, int *mem_rects, int *cur_bboxes,
+                                    int *cur_rects, void *workspace, size_t workspace_bytes, float *clear, int n_clear,
+                                    void *stream) {
   int rc = check_common(prev_mask, B, K, H, W, mem_bboxes, workspace, workspace_bytes);
   if (rc) return rc;
   RMNET_CHECK_ARG(flow && cur_bboxes && mem_rects && cur_rects, "null pointer argument");
@@ -596,8 +615,9 @@ int rmnet_frame_regions_forward(const float *prev_mask, const float *flow, int B
   make_finalize(fw, false, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, k_scan, cur_rects);
   make_finalize(fd, true, H, W, pad_l, pad_r, pad_t, pad_b, prob_threshold, n_pts_threshold, n_bbox_loose_pixels, k_scan, mem_rects);
   return launch_frame_boxes(prev_mask, flow, B, K, H, W, sampler, prob_threshold, fw, cur_bboxes, &fd, mem_bboxes, workspace,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, clear, n_clear);
 }
+extern "C" {
 
 int rmnet_warp_att_map_forward(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
                                float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int *bboxes,

@@ -39,6 +39,59 @@ void count_launch(int n = 1);
     RMNET_CUDA(cudaGetLastError());                \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------------
+// The kernels of one frame step form a chain on one stream; each is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization so that its launch latency and its independent prologue overlap
+// the tail of its predecessor.  Device side: pdl_wait() blocks until the predecessor grid has completed and its
+// writes are visible; pdl_trigger() lets the successor start launching.  Rule used throughout: a kernel triggers only
+// AFTER its own wait, so when a successor's pre-wait code runs, everything two or more links up the chain is complete.
+// Both are no-ops for a kernel launched without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();  // runtime.cu: false when the environment sets RMNET_DISABLE_PDL=1 (debugging aid)
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        bool pdl, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl && pdl_enabled()) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// internal cross-file entry points of the frame-step chain (att_map.cu, bank.cu)
+int frame_regions_chain_head(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
+                             float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t,
+                             int pad_b, int k_scan, int *mem_bboxes, int *mem_rects, int *cur_bboxes, int *cur_rects,
+                             void *workspace, size_t workspace_bytes, float *clear, int n_clear, void *stream);
+// Query side of one read (models/rmnet.py:355-358, :163), produced by roles of the pack kernel (bank.cu):
+//   qhi/qlo [n_obj][nq_pad][128]: region-compacted 16-bit hi/lo planes of k4e * att16 (rows up to the next 128 zeroed),
+//   mem_val[:, 512:1024] = q_val * att16.
+struct QuerySide {
+  const float *q_key, *q_val;
+  long long q_key_obj_stride, q_val_obj_stride;  // floats; 0 = one query frame shared by all objects (:332-333)
+  const int *q_rects;                            // [n_obj,4] cell rectangles, nullptr = dense
+  uint16_t *qhi, *qlo;
+  int nq_pad;
+  int vec4;                                      // 128-bit accesses allowed for q_val / mem_val
+  float *mem_val;
+};
+int bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *k4, long long k_obj_stride,
+                       long long k_ch_stride, const float *v4, long long v_obj_stride, long long v_ch_stride, const int *rects,
+                       int n_obj, int h, int w, int elem_format, int commit, bool chained, const QuerySide *query_side,
+                       void *stream);
+int launch_query_side(const QuerySide &qs, int n_obj, int h, int w, int elem_format, cudaStream_t st);
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
@@ -94,7 +147,8 @@ static inline BankView bank_view(void *bank, int n_slots, int cap) {
 // opart [n_splits][n_obj][512][nq_pad] f32 (unnormalised numerators), ml [n_splits][n_obj][2 halves][nq_pad][2] f32
 struct ReadWorkspace {
   float *opart, *ml;
-  int *sched;  // [SCHED_MAX_OBJ] partial slots per object, written by the tcgen05 kernel for merge.cu
+  int *sched;           // [SCHED_MAX_OBJ] partial slots per object, written by the tcgen05 kernel for merge.cu
+  uint16_t *qhi, *qlo;  // [n_obj][nq_pad][128] packed query keys (QuerySide)
   int n_splits, nq_pad;
   size_t total;
 };
@@ -110,6 +164,10 @@ static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_spl
   o = align_up(o + (size_t)W.n_splits * n_obj * 2 * W.nq_pad * 2 * sizeof(float), 1024);
   W.sched = (int *)((char *)ws + o);
   o = align_up(o + 64 * sizeof(int), 1024);
+  W.qhi = (uint16_t *)((char *)ws + o);
+  o = align_up(o + (size_t)n_obj * W.nq_pad * RMNET_CK * sizeof(uint16_t), 1024);
+  W.qlo = (uint16_t *)((char *)ws + o);
+  o = align_up(o + (size_t)n_obj * W.nq_pad * RMNET_CK * sizeof(uint16_t), 1024);
   W.total = o;
   return W;
 }
@@ -187,6 +245,7 @@ struct SchedTable {
   int nt[SCHED_MAX_OBJ];         // KV tiles of object o
   int nqt[SCHED_MAX_OBJ];        // query tiles of object o
   int ns[SCHED_MAX_OBJ];         // KV chunks (= partial slots) of object o
+  int count[SCHED_MAX_OBJ];      // stored cells of object o (committed + temporary frame)
   int ibase[SCHED_MAX_OBJ + 1];  // first item of object o
 };
 // ceil(a / b) for 0 < b, a < 2^20 via one float multiply and a fix-up (a 32-bit integer division costs ~25 instructions)
@@ -198,8 +257,11 @@ __device__ __forceinline__ unsigned ceil_div_small(unsigned a, unsigned b, float
   return q;
 }
 // Called by ONE FULL WARP (all 32 lanes); lane 0 writes the table.  G = number of persistent CTAs.
+// temp_rects != nullptr (rmnet_frame_step without commit): the temporary frame's cell count is derived from its cell
+// rectangle exactly as bank_pack_kernel derives it, so the table can be built BEFORE the pack kernel has finished
+// (the committed counters do not change during such a step).
 __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
-                                            int n_obj, int h, int w, int G) {
+                                            const int *__restrict__ temp_rects, int cap, int n_obj, int h, int w, int G) {
   const int lane = threadIdx.x & 31;
   // per-object tile counts (lanes over objects), also kept in registers for the candidate evaluation
   int max_nt = 0;
@@ -208,11 +270,19 @@ __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict
     int nt = 0, nqt = 0;
     if (o < n_obj) {
       const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-      const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
+      int count;
+      if (temp_rects) {
+        const int base = bank_meta[o * 8 + META_CELLS_C];
+        const int r = rect_cells(__ldg(reinterpret_cast<const int4 *>(temp_rects) + o));
+        count = base + (base + r > cap ? 0 : r);  // bank_pack_kernel drops a frame that would overflow the bank
+      } else {
+        count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
+      }
       nt = (count + KV_TILE - 1) / KV_TILE;
       nqt = (rect_cells(qr) + UMMA_QT - 1) / UMMA_QT;
       T.nt[o] = nt;
       T.nqt[o] = nqt;
+      T.count[o] = count;
     }
     max_nt = max(max_nt, __reduce_max_sync(0xffffffffu, nqt > 0 ? nt : 0));
   }

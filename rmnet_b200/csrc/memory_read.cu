@@ -5,17 +5,71 @@ namespace rmnet {
 int launch_memory_read_simt(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st);
-int launch_memory_read_umma(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
-                            int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
-                            cudaStream_t st);
-int launch_merge(const BankView &bank, const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h,
-                 int w, int n_splits, bool device_sched, const ReadWorkspace &W, float *mem_val, cudaStream_t st);
+int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int fmt, int precision,
+                            int n_splits, const ReadWorkspace &W, const int *temp_rects, bool pdl, cudaStream_t st);
+int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
+                 const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st);
 bool umma_supported(int cap_cells);
 
 namespace {
 __global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) reinterpret_cast<int4 *>(rects)[i] = make_int4(0, w - 1, 0, h - 1);
+}
+
+
+QuerySide make_query_side(const float *q_key, const float *q_val, long long q_key_obj_stride, const int *q_rects,
+                          const ReadWorkspace &W, int N, float *mem_val) {
+  QuerySide qs;
+  qs.q_key = q_key;
+  qs.q_val = q_val;
+  qs.q_key_obj_stride = q_key_obj_stride;
+  qs.q_val_obj_stride = q_key_obj_stride ? (q_key_obj_stride / RMNET_CK) * RMNET_CV : 0;
+  qs.q_rects = q_rects;
+  qs.qhi = W.qhi;
+  qs.qlo = W.qlo;
+  qs.nq_pad = W.nq_pad;
+  qs.vec4 = (N % 4 == 0 && (uintptr_t)q_val % 16 == 0 && (uintptr_t)mem_val % 16 == 0 && qs.q_val_obj_stride % 4 == 0) ? 1 : 0;
+  qs.mem_val = mem_val;
+  return qs;
+}
+
+// chained = true: called from rmnet_frame_step, the launches are programmatic dependents of the pack / commit kernel.
+// temp_rects (optional, chained only): the cell rectangles the pack kernel is storing as the temporary frame.
+int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
+                          const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h, int w,
+                          int elem_format, int precision, int impl, int stages, float *mem_val, void *workspace,
+                          size_t workspace_bytes, const int *temp_rects, bool chained, void *stream) {
+  RMNET_CHECK_ARG(bank && q_key && q_val && mem_val && workspace, "null pointer argument");
+  RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
+  RMNET_CHECK_ARG(n_obj <= 65535, "too many objects");
+  RMNET_CHECK_ARG(elem_format == 0 || elem_format == 1, "elem_format must be 0 (bf16) or 1 (fp16)");
+  RMNET_CHECK_ARG(precision == RMNET_PREC_SPLIT3 || precision == RMNET_PREC_SINGLE, "bad precision mode");
+  RMNET_CHECK_ARG(q_rects == nullptr || (uintptr_t)q_rects % 16 == 0, "q_rects must be 16-byte aligned");
+  BankLayout L = bank_layout(n_slots, cap_cells);
+  if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
+  cudaStream_t st = (cudaStream_t)stream;
+  BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
+  if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
+  RMNET_CHECK_ARG(impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
+  const int n_splits = impl == RMNET_IMPL_UMMA ? READ_MAX_SPLITS : pick_splits(n_obj, h * w, 64, cap_cells);
+  ReadWorkspace W = read_workspace(workspace, n_obj, h * w, n_splits);
+  if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
+  RMNET_CHECK_ARG(stages >= 1 && stages <= RMNET_STAGE_ALL, "bad stages mask %d", stages);
+  int rc = RMNET_OK;
+  const bool umma = impl == RMNET_IMPL_UMMA;
+  if (stages & RMNET_STAGE_QUERY) {  // (rmnet_frame_step folds this into its pack launch instead)
+    QuerySide qs = make_query_side(q_key, q_val, q_obj_stride, q_rects, W, h * w, mem_val);
+    if ((rc = launch_query_side(qs, n_obj, h, w, elem_format, st))) return rc;
+  }
+  if (!(stages & RMNET_STAGE_PARTIAL)) {
+  } else if (umma)
+    rc = launch_memory_read_umma(bv, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, temp_rects, chained, st);
+  else
+    rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
+  if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
+  // the merge is a programmatic dependent of the tcgen05 kernel whenever both run in this call
+  return launch_merge(bv, q_rects, n_obj, h, w, n_splits, umma, W, mem_val, umma && (stages & RMNET_STAGE_PARTIAL), st);
 }
 
 }  // namespace
@@ -35,33 +89,9 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
                            const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h, int w,
                            int elem_format, int precision, int impl, int stages, float *mem_val, void *workspace,
                            size_t workspace_bytes, void *stream) {
-  RMNET_CHECK_ARG(bank && q_key && q_val && mem_val && workspace, "null pointer argument");
-  RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
-  RMNET_CHECK_ARG(n_obj <= 65535, "too many objects");
-  RMNET_CHECK_ARG(elem_format == 0 || elem_format == 1, "elem_format must be 0 (bf16) or 1 (fp16)");
-  RMNET_CHECK_ARG(precision == RMNET_PREC_SPLIT3 || precision == RMNET_PREC_SINGLE, "bad precision mode");
-  RMNET_CHECK_ARG(q_rects == nullptr || (uintptr_t)q_rects % 16 == 0, "q_rects must be 16-byte aligned");
-  BankLayout L = bank_layout(n_slots, cap_cells);
-  if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
-  cudaStream_t st = (cudaStream_t)stream;
-  BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
-  if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
-  RMNET_CHECK_ARG(impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
-  const int n_splits = impl == RMNET_IMPL_UMMA ? READ_MAX_SPLITS : pick_splits(n_obj, h * w, 64, cap_cells);
-  ReadWorkspace W = read_workspace(workspace, n_obj, h * w, n_splits);
-  if (workspace_bytes < W.total) { set_error("workspace too small: %zu < %zu", workspace_bytes, W.total); return RMNET_E_WORKSPACE; }
-  RMNET_CHECK_ARG(stages >= 1 && stages <= 3, "bad stages mask %d", stages);
-  int rc = RMNET_OK;
-  if (!(stages & RMNET_STAGE_PARTIAL)) {
-  } else if (impl == RMNET_IMPL_UMMA)
-    rc = launch_memory_read_umma(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
-  else
-    rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
-  if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
-  return launch_merge(bv, q_val, q_obj_stride ? (q_obj_stride / RMNET_CK) * RMNET_CV : 0, q_rects, n_obj, h, w, n_splits,
-                      impl == RMNET_IMPL_UMMA, W, mem_val, st);
+  return bank_memory_read_impl(bank, bank_bytes, n_slots, cap_cells, q_key, q_val, q_obj_stride, q_rects, n_obj, h, w, elem_format,
+                               precision, impl, stages, mem_val, workspace, workspace_bytes, nullptr, false, stream);
 }
-
 
 int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask, const float *flow,
                      int K, int H, int W, int sampler, float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels,
@@ -73,15 +103,30 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   const int h = (H + pad_t + pad_b) / 16, w = (W + pad_l + pad_r) / 16;
   const long long N = (long long)h * w;
   int *mem_bb = boxes_out, *mem_rc = boxes_out + 4 * K, *cur_bb = boxes_out + 8 * K, *cur_rc = boxes_out + 12 * K;
-  int rc = rmnet_frame_regions_forward(prev_mask, flow, 1, K, H, W, sampler, prob_threshold, n_pts_threshold,
-                                       n_bbox_loose_pixels, pad_l, pad_r, pad_t, pad_b, k_scan, mem_bb, mem_rc, cur_bb, cur_rc,
-                                       box_workspace, box_workspace_bytes, stream);
+  RMNET_CHECK_ARG(bank && n_slots > 0 && cap_cells > 0 && n_obj <= n_slots, "bad bank argument");
+  BankLayout L = bank_layout(n_slots, cap_cells);
+  if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
+  BankView bv = bank_view(bank, n_slots, cap_cells);
+  // One programmatic-dependent-launch chain: regions (also zeroes the temporary value sums) -> pack [-> commit] -> tcgen05
+  // read -> merge.  Each kernel's launch latency and independent prologue overlap its predecessor's tail.
+  int rc = frame_regions_chain_head(prev_mask, flow, 1, K, H, W, sampler, prob_threshold, n_pts_threshold, n_bbox_loose_pixels,
+                                    pad_l, pad_r, pad_t, pad_b, k_scan, mem_bb, mem_rc, cur_bb, cur_rc, box_workspace,
+                                    box_workspace_bytes, bv.vsum + (size_t)n_slots * RMNET_CV, n_slots * RMNET_CV, stream);
   if (rc) return rc;
-  rc = rmnet_bank_memorize(bank, bank_bytes, n_slots, cap_cells, k4, RMNET_CK * N, N, v4, RMNET_CV * N, N, mem_rc + 4, n_obj,
-                           h, w, elem_format, commit, stream);
+  RMNET_CHECK_ARG(q_key && q_val && mem_val && read_workspace, "null pointer argument");
+  RMNET_CHECK_ARG(impl == RMNET_IMPL_AUTO || impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
+  const bool umma = impl == RMNET_IMPL_UMMA || (impl == RMNET_IMPL_AUTO && umma_supported(cap_cells));
+  ReadWorkspace RW = rmnet::read_workspace(read_workspace, n_obj, (int)N, umma ? READ_MAX_SPLITS : pick_splits(n_obj, (int)N, 64, cap_cells));
+  if (read_workspace_bytes < RW.total) { set_error("workspace too small: %zu < %zu", read_workspace_bytes, RW.total); return RMNET_E_WORKSPACE; }
+  // the pack launch also prepares the query side (packed query keys, q_val passthrough) of this frame's read
+  QuerySide qs = make_query_side(q_key, q_val, 0, cur_rc + 4, RW, (int)N, mem_val);
+  rc = bank_memorize_impl(bank, bank_bytes, n_slots, cap_cells, k4, RMNET_CK * N, N, v4, RMNET_CV * N, N, mem_rc + 4, n_obj, h, w,
+                          elem_format, commit, /*chained=*/true, &qs, stream);
   if (rc) return rc;
-  return rmnet_bank_memory_read(bank, bank_bytes, n_slots, cap_cells, q_key, q_val, 0, cur_rc + 4, n_obj, h, w, elem_format,
-                                precision, impl, RMNET_STAGE_ALL, mem_val, read_workspace, read_workspace_bytes, stream);
+  // without a commit the committed counters are stable, so the read kernel can build its schedule before the pack finishes
+  return bank_memory_read_impl(bank, bank_bytes, n_slots, cap_cells, q_key, q_val, 0, cur_rc + 4, n_obj, h, w, elem_format,
+                               precision, impl, RMNET_STAGE_PARTIAL | RMNET_STAGE_MERGE, mem_val, read_workspace,
+                               read_workspace_bytes, commit ? nullptr : mem_rc + 4, /*chained=*/true, stream);
 }
 
 static size_t reader_scratch_layout(int n, int T, int h, int w, size_t *off_rects, size_t *off_read, int *cap) {

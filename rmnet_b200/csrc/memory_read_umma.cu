@@ -195,10 +195,10 @@ template <int FMT, bool USE_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
-                        const int *__restrict__ bank_meta, const float *__restrict__ q_key, long long q_obj_stride,
+                        const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
                         const int *__restrict__ q_rects, int h, int w,
                         float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
-                        int n_obj, float *__restrict__ dbg) {
+                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -208,15 +208,14 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
 
   long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 16 : nullptr;  // dev hook
   if (tstamp && threadIdx.x == 128) tstamp[0] = clock64();
-  const int N = h * w;
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1)
+  // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1).
+  //      Chained launch (PDL): everything up to pdl_wait() overlaps the tail of the pack kernel.
   if (tstamp && threadIdx.x == 96) tstamp[8] = clock64();
-  if (warp == 3) sched_build(sched, bank_meta, q_rects, n_obj, h, w, (int)gridDim.x);
-  if (tstamp && threadIdx.x == 96) tstamp[9] = clock64();
+  if (warp == 3 && temp_rects) sched_build(sched, bank_meta, q_rects, temp_rects, cap, n_obj, h, w, (int)gridDim.x);
   if (tstamp && threadIdx.x == 32) tstamp[10] = clock64();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
@@ -235,6 +234,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tstamp && threadIdx.x == 32) tstamp[11] = clock64();
+  pdl_wait();
+  pdl_trigger();
+  if (warp == 3 && !temp_rects) sched_build(sched, bank_meta, q_rects, nullptr, cap, n_obj, h, w, (int)gridDim.x);
+  if (tstamp && threadIdx.x == 96) tstamp[9] = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -361,43 +364,86 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
     int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
     bool first_piece = true;
-    float xq[RMNET_CK];  // this row's 128 query-key channels, fetched one item ahead (overlaps the previous epilogue)
+    // this row's 128 query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's
+    // query role in the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that
+    // each of the loads below is one coalesced 512 B access per warp
+    uint32_t qh[RMNET_CK / 2], ql[USE_LO ? RMNET_CK / 2 : 1];
     auto fetch_q = [&](const Piece &p) {
-      const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + p.o) : make_int4(0, w - 1, 0, h - 1);
-      const int nn = p.qtile * QT + row;
-      // rows past the region's last query read cell 0: finite garbage that no one consumes (rows are independent)
-      const float *qp = q_key + (long long)p.o * q_obj_stride + (nn < rect_cells(qr) ? rect_pos(qr, nn, w) : 0);
+      const size_t r = ((size_t)p.o * nq_pad + p.qtile * QT + (row & ~31)) * (RMNET_CK / 8) + (row & 31);  // uint4 units
+      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r, *pl = reinterpret_cast<const uint4 *>(qlo) + r;
 #pragma unroll
-      for (int j = 0; j < RMNET_CK; ++j) xq[j] = __ldg(qp + j * N);  // 32-bit offsets: one IMAD.WIDE per load
+      for (int j = 0; j < RMNET_CK / 8; ++j) {
+        const uint4 v = __ldg(ph + j * 32);
+        qh[4 * j] = v.x; qh[4 * j + 1] = v.y; qh[4 * j + 2] = v.z; qh[4 * j + 3] = v.w;
+      }
+      if (USE_LO) {
+#pragma unroll
+        for (int j = 0; j < RMNET_CK / 8; ++j) {
+          const uint4 v = __ldg(pl + j * 32);
+          ql[4 * j] = v.x; ql[4 * j + 1] = v.y; ql[4 * j + 2] = v.z; ql[4 * j + 3] = v.w;
+        }
+      }
     };
+    // One code site per phase.  Order per piece k:  [Q(k) -> TMEM]  [drain O(k-1)]  [tiles of k]  -- so the tensor pipe
+    // already computes S(k, 0..1) while the numerators of piece k-1 leave TMEM, and the prefetched Q registers are dead
+    // before the drain needs its own.
     Piece nxt;
-    bool have = iter.next(pc);
+    bool have_cur = false, have_nxt = iter.next(nxt);
+    int gt_done = 0;  // tile counter at the end of the current piece (parity of its last pv_done)
     if (tstamp && row == 0) tstamp[12] = clock64();
-    if (have) fetch_q(pc);
-    if (tstamp && row == 0) tstamp[13] = clock64();
-    while (have) {
+    for (;;) {
+      if (have_nxt) {
+        // ---- Q rows of the next piece -> 16-bit hi/lo planes in TMEM (A operand of the score product).  All score
+        //      MMAs of the current piece have retired (its last softmax pass waited on their commit) and its P.V
+        //      MMAs do not read Q.
+        fetch_q(nxt);
+        if (tstamp && first_piece && row == 0) tstamp[13] = clock64();
+#pragma unroll
+        for (int c = 0; c < RMNET_CK / 2; c += 16) {
+          TMEM_ST16(t_base + TM_Q_HI + c, qh, c);
+          if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c, ql, c);
+        }
+        if (tstamp && first_piece && row == 0) tstamp[14] = clock64();
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(smem_u32(&bars->q_ready));
+        if (tstamp && first_piece && row == 0) tstamp[2] = clock64();
+      }
+      if (have_cur) {
+        // ---- epilogue of the current piece: unnormalised numerators for merge.cu, partial slot pc.slot
+        const int n = pc.qtile * QT + row;
+        mbar_wait(smem_u32(&bars->pv_done[(gt_done - 1) & 1]), ((gt_done - 1) >> 1) & 1);
+        tc_fence_after();
+        if (tstamp && first_piece && row == 0) tstamp[5] = clock64();
+        float *ob = opart + (((size_t)pc.slot * n_obj + pc.o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
+        // software pipeline over 32-column groups: the TMEM load of group g+1 is in flight while group g is stored
+        uint32_t ra[32], rb[32];
+        TMEM_LD16(t_base + TM_O, ra, 0);
+        TMEM_LD16(t_base + TM_O + 16, ra, 16);
+#pragma unroll 1
+        for (int c = 0; c < CVH; c += 64) {
+          tc_wait_ld();
+          TMEM_LD16(t_base + TM_O + c + 32, rb, 0);
+          TMEM_LD16(t_base + TM_O + c + 48, rb, 16);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(ra[j]);  // lanes run along queries: coalesced
+          tc_wait_ld();
+          if (c + 64 < CVH) {
+            TMEM_LD16(t_base + TM_O + c + 64, ra, 0);
+            TMEM_LD16(t_base + TM_O + c + 80, ra, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ob[(c + 32 + j) * nq_pad] = __uint_as_float(rb[j]);
+        }
+        if (tstamp && first_piece && row == 0) tstamp[6] = clock64();
+        first_piece = false;
+      }
+      if (!have_nxt) break;
+      pc = nxt;
+      have_cur = true;
       const int o = pc.o;
       const int n = pc.qtile * QT + row;
-      const int count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
-
-      // ---- Q rows -> 16-bit hi/lo planes in TMEM (A operand of the score product).  All score MMAs of the previous
-      //      piece have retired: its last softmax pass waited on their commit.
-#pragma unroll
-      for (int c0 = 0; c0 < RMNET_CK; c0 += 32) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          lo[j] = 0;
-          split_pack2<FMT, USE_LO>(xq[c0 + 2 * j], xq[c0 + 2 * j + 1], hi[j], lo[j]);
-        }
-        TMEM_ST16(t_base + TM_Q_HI + c0 / 2, hi, 0);
-        if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c0 / 2, lo, 0);
-      }
-      if (tstamp && first_piece && row == 0) tstamp[14] = clock64();
-      tc_wait_st();
-      tc_fence_before();
-      mbar_arrive(smem_u32(&bars->q_ready));
-      if (tstamp && first_piece && row == 0) tstamp[2] = clock64();
+      const int count = sched.count[o];
 
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int it = 0; it < pc.n_it; ++it, ++gt) {
@@ -475,32 +521,15 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[b]));
       }
-
-      // ---- epilogue of the piece: unnormalised numerators + (max, sum) statistics for merge.cu, partial slot pc.slot
+      gt_done = gt;
+      // (max, sum) statistics of the piece for merge.cu
       {
         float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)pc.slot * n_obj + o) * 2 + pc.half) * nq_pad + n;
         *dst = make_float2(m_ref, l_sum);
       }
-      if (tstamp && first_piece && row == 0) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
-      have = iter.next(nxt);
-      if (have) fetch_q(nxt);  // global loads of the next item's Q fly while O is drained below
-      mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
-      tc_fence_after();
-      if (tstamp && first_piece && row == 0) tstamp[5] = clock64();
-      float *ob = opart + (((size_t)pc.slot * n_obj + o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
-#pragma unroll 1
-      for (int c = 0; c < CVH; c += 32) {
-        uint32_t orr[32];
-        TMEM_LD16(t_base + TM_O + c, orr, 0);
-        TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(orr[j]);  // lanes run along queries: coalesced
-      }
       if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
-      if (tstamp && first_piece && row == 0) tstamp[6] = clock64();
-      first_piece = false;
-      pc = nxt;
+      if (tstamp && first_piece && row == 0) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
+      have_nxt = iter.next(nxt);
     }
   }
 
@@ -560,9 +589,8 @@ int umma_grid_size() {
   return n_sms;
 }
 
-int launch_memory_read_umma(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
-                            int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
-                            cudaStream_t st) {
+int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int fmt, int precision,
+                            int n_splits, const ReadWorkspace &W, const int *temp_rects, bool pdl, cudaStream_t st) {
   RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
   RMNET_CHECK_ARG(n_obj <= SCHED_MAX_OBJ, "tcgen05 path supports at most %d objects per call", (int)SCHED_MAX_OBJ);
   CUtensorMap mkh, mkl, mvh, mvl;
@@ -581,8 +609,9 @@ int launch_memory_read_umma(const BankView &bank, const float *q_key, long long 
   do {                                                                                                                   \
     RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                     (int)SMEM_BYTES));                                                                   \
-    memory_read_umma_kernel<F, L><<<grid, kThreads, SMEM_BYTES, st>>>(mkh, mkl, mvh, mvl, bank.meta, q_key, q_obj_stride, \
-                                                                      q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj, g_dbg); \
+    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
+                             bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
+                             temp_rects, bank.cap, g_dbg));                                                              \
   } while (0)
   if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
   else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);

@@ -1,5 +1,6 @@
 // runtime.cu -- error string, launch counter, ABI version.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,11 @@ void set_error(const char *fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+// Read on every launch (a getenv of a short name: negligible next to a kernel launch) so a test can flip it.
+bool pdl_enabled() {
+  const char *e = getenv("RMNET_DISABLE_PDL");
+  return !(e && e[0] == '1');
+}
 }  // namespace rmnet
 
 extern "C" {

@@ -223,7 +223,7 @@ class MemoryBank:
         else:
             self.has_temp = True
 
-    def read(self, q_key, q_val, q_rects, n_obj, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, stages=3, out=None):
+    def read(self, q_key, q_val, q_rects, n_obj, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, stages=7, out=None):
         """q_key [128,h,w] / q_val [512,h,w] (one frame shared by all objects) or [n,128,h,w] / [n,512,h,w];
         q_rects [n,4] int32 or None (dense) -> mem_val [n,1024,h,w]."""
         _require(q_key, "q_key")

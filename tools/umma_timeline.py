@@ -34,5 +34,12 @@ for wlname in ("c2", "c3"):
     ex = (t[:, 8:15] - t[:, :1]).astype(np.float64)
     for i, nm in enumerate(["sched begin", "sched end", "alloc begin", "alloc end", "iter.next done", "Q loads issued", "Q converted+stored (before wait::st)"]):
         print(f"      .. {nm:38s} {np.median(ex[:, i]):9.0f}")
+    order = np.argsort(rel[:, 5])
+    print("   tiles of the first item, by CTA end time:", " ".join(f"{int(a)}" for a in t[order, 7][::4]))
+    print("   end cycles (every 4th CTA):            ", " ".join(f"{int(a/1000)}" for a in rel[order, 5][::4]))
+    _, rq = rmnet_b200.ops.regional_boxes(d["mask"][None], d["flow"][None], padded_frame=False)
+    rqn = rq[0, 1:n + 1].cpu().numpy()
+    st = rm.bank.stats()
+    print("   cells/object", (st[:n, 0] + st[:n, 1]).tolist(), "query cells/object", [int(max(0, r[1]-r[0]+1) * max(0, r[3]-r[2]+1)) for r in rqn])
     per_tile = (rel[:, 3] - rel[:, 2]) / np.maximum(t[:, 7] - 1, 1)
     print(f"   steady state cycles per tile (median) {np.median(per_tile):.0f}")
