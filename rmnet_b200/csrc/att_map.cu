@@ -328,62 +328,80 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
   for (int k = threadIdx.x; k < 2 * K * 5; k += kThreads) s_acc[k] = 0;
   __syncthreads();
 
-  const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
-  const bool live = j < n_pixels;
-  const long long jj = live ? j : n_pixels - 1;
-  const int y = (int)(jj / W), x = (int)(jj - (long long)y * W);
+  // Persistent CTAs (one wave, launch_frame_boxes sizes the grid): each walks pixel tiles of kThreads consecutive pixels;
+  // the flow of the NEXT tile is loaded before the gathers of the current one are consumed.
+  const long long n_tiles = (n_pixels + kThreads - 1) / kThreads;
   const int lane = threadIdx.x & 31;
-  const int x_lane0 = __shfl_sync(0xffffffffu, x, 0), y_lane0 = __shfl_sync(0xffffffffu, y, 0);
-  const bool one_row = __shfl_sync(0xffffffffu, y, 31) == y_lane0 && __all_sync(0xffffffffu, live);
-  const Tap t = make_tap<ORDER>(x, y, __ldg(fl + jj), __ldg(fl + n_pixels + jj), H, W, inv_w, inv_h);
-  const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
-  const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
-  const bool p_nw = xin0 && yin0, p_ne = xin1 && yin0, p_sw = xin0 && yin1, p_se = xin1 && yin1;
-  // 32-bit in-plane offsets; an out-of-bounds tap reads the thread's own pixel instead and is then replaced by 0
-  // (selected, not multiplied: a NaN there must not leak), so the loop body has no address predication.
-  const int o_self = (int)jj;
-  const int o_nw = t.y0 * W + t.x0;
-  const int a_nw = p_nw ? o_nw : o_self, a_ne = p_ne ? o_nw + 1 : o_self;
-  const int a_sw = p_sw ? o_nw + W : o_self, a_se = p_se ? o_nw + W + 1 : o_self;
-  const float *plane = prev_mask + ((long long)b * K + 1) * n_pixels;  // channel 1; advanced by n_pixels per channel
-
   const int Ks = fin_warp.k_scan;  // channels >= Ks are known to be empty (absent objects): not read at all
-  for (int i0 = 1; i0 < Ks; i0 += kChunkCh) {
-    const int nch = min(kChunkCh, Ks - i0);  // warp-uniform
-    float v_nw[kChunkCh], v_ne[kChunkCh], v_sw[kChunkCh], v_se[kChunkCh], v_d[kChunkCh];
-    {
-      const float *pl = plane;
+  long long tile = blockIdx.x;
+  float fx_n = 0.f, fy_n = 0.f;
+  if (tile < n_tiles) {
+    const long long jn = min(tile * kThreads + threadIdx.x, n_pixels - 1);
+    fx_n = __ldg(fl + jn);
+    fy_n = __ldg(fl + n_pixels + jn);
+  }
+  for (; tile < n_tiles; tile += gridDim.x) {
+    const long long j = tile * kThreads + threadIdx.x;
+    const bool live = j < n_pixels;
+    const long long jj = live ? j : n_pixels - 1;
+    const float fx = fx_n, fy = fy_n;
+    if (tile + gridDim.x < n_tiles) {
+      const long long jn = min((tile + gridDim.x) * kThreads + threadIdx.x, n_pixels - 1);
+      fx_n = __ldg(fl + jn);
+      fy_n = __ldg(fl + n_pixels + jn);
+    }
+    const int y = (int)(jj / W), x = (int)(jj - (long long)y * W);
+    const int x_lane0 = __shfl_sync(0xffffffffu, x, 0), y_lane0 = __shfl_sync(0xffffffffu, y, 0);
+    const bool one_row = __shfl_sync(0xffffffffu, y, 31) == y_lane0 && __all_sync(0xffffffffu, live);
+    const Tap t = make_tap<ORDER>(x, y, fx, fy, H, W, inv_w, inv_h);
+    const bool xin0 = t.x0 >= 0 && t.x0 < W, xin1 = t.x0 + 1 >= 0 && t.x0 + 1 < W;
+    const bool yin0 = t.y0 >= 0 && t.y0 < H, yin1 = t.y0 + 1 >= 0 && t.y0 + 1 < H;
+    const bool p_nw = xin0 && yin0, p_ne = xin1 && yin0, p_sw = xin0 && yin1, p_se = xin1 && yin1;
+    // 32-bit in-plane offsets; an out-of-bounds tap reads the thread's own pixel instead and is then replaced by 0
+    // (selected, not multiplied: a NaN there must not leak), so the loop body has no address predication.
+    const int o_self = (int)jj;
+    const int o_nw = t.y0 * W + t.x0;
+    const int a_nw = p_nw ? o_nw : o_self, a_ne = p_ne ? o_nw + 1 : o_self;
+    const int a_sw = p_sw ? o_nw + W : o_self, a_se = p_se ? o_nw + W + 1 : o_self;
+    const float *plane = prev_mask + ((long long)b * K + 1) * n_pixels;  // channel 1; advanced by n_pixels per channel
+
+    for (int i0 = 1; i0 < Ks; i0 += kChunkCh) {
+      const int nch = min(kChunkCh, Ks - i0);  // warp-uniform
+      float v_nw[kChunkCh], v_ne[kChunkCh], v_sw[kChunkCh], v_se[kChunkCh], v_d[kChunkCh];
+      {
+        const float *pl = plane;
 #pragma unroll
-      for (int u = 0; u < kChunkCh; ++u) {
-        if (u < nch) {
-          v_nw[u] = __ldg(pl + a_nw);
-          v_ne[u] = __ldg(pl + a_ne);
-          v_sw[u] = __ldg(pl + a_sw);
-          v_se[u] = __ldg(pl + a_se);
-          if (DIRECT) v_d[u] = __ldg(pl + o_self);
-          pl += n_pixels;
+        for (int u = 0; u < kChunkCh; ++u) {
+          if (u < nch) {
+            v_nw[u] = __ldg(pl + a_nw);
+            v_ne[u] = __ldg(pl + a_ne);
+            v_sw[u] = __ldg(pl + a_sw);
+            v_se[u] = __ldg(pl + a_se);
+            if (DIRECT) v_d[u] = __ldg(pl + o_self);
+            pl += n_pixels;
+          }
         }
       }
-    }
 #pragma unroll
-    for (int u = 0; u < kChunkCh; ++u) {
-      if (u >= nch) break;  // warp-uniform
-      const int i = i0 + u;
-      // same FMA chain as sample_tap (an out-of-bounds tap contributes fma(0, w, acc) = acc exactly)
-      const float x_nw = p_nw ? v_nw[u] : 0.f, x_ne = p_ne ? v_ne[u] : 0.f;
-      const float x_sw = p_sw ? v_sw[u] : 0.f, x_se = p_se ? v_se[u] : 0.f;
-      float acc;
-      if (ORDER == 1) acc = __fmaf_rn(x_ne, t.ne, __fmul_rn(x_nw, t.nw));
-      else acc = __fmaf_rn(x_nw, t.nw, __fmul_rn(x_ne, t.ne));
-      acc = __fmaf_rn(x_se, t.se, __fmaf_rn(x_sw, t.sw, acc));
-      const bool hit_w = live && (__fmul_rn(acc, t.valid) >= thr);
-      warp_box_to_smem(s_acc + i * 5, __ballot_sync(0xffffffffu, hit_w), one_row, x_lane0, y_lane0, hit_w, x, y, lane);
-      if (DIRECT) {
-        const bool hit_d = live && (v_d[u] >= thr);
-        warp_box_to_smem(s_acc + (K + i) * 5, __ballot_sync(0xffffffffu, hit_d), one_row, x_lane0, y_lane0, hit_d, x, y, lane);
+      for (int u = 0; u < kChunkCh; ++u) {
+        if (u >= nch) break;  // warp-uniform
+        const int i = i0 + u;
+        // same FMA chain as sample_tap (an out-of-bounds tap contributes fma(0, w, acc) = acc exactly)
+        const float x_nw = p_nw ? v_nw[u] : 0.f, x_ne = p_ne ? v_ne[u] : 0.f;
+        const float x_sw = p_sw ? v_sw[u] : 0.f, x_se = p_se ? v_se[u] : 0.f;
+        float acc;
+        if (ORDER == 1) acc = __fmaf_rn(x_ne, t.ne, __fmul_rn(x_nw, t.nw));
+        else acc = __fmaf_rn(x_nw, t.nw, __fmul_rn(x_ne, t.ne));
+        acc = __fmaf_rn(x_se, t.se, __fmaf_rn(x_sw, t.sw, acc));
+        const bool hit_w = live && (__fmul_rn(acc, t.valid) >= thr);
+        warp_box_to_smem(s_acc + i * 5, __ballot_sync(0xffffffffu, hit_w), one_row, x_lane0, y_lane0, hit_w, x, y, lane);
+        if (DIRECT) {
+          const bool hit_d = live && (v_d[u] >= thr);
+          warp_box_to_smem(s_acc + (K + i) * 5, __ballot_sync(0xffffffffu, hit_d), one_row, x_lane0, y_lane0, hit_d, x, y, lane);
+        }
       }
+      plane += (long long)kChunkCh * n_pixels;
     }
-    plane += (long long)kChunkCh * n_pixels;
   }
   __syncthreads();
   // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it.  Only the threads that publish
@@ -517,7 +535,11 @@ static int launch_frame_boxes(const float *prev_mask, const float *flow, int B, 
                               void *workspace, cudaStream_t st, float *clear = nullptr, int n_clear = 0) {
   const float inv_w = 1.0f / (float)(W - 1 > 1 ? W - 1 : 1);  // models/rmnet.py:265 max(W-1,1); host fp32 reciprocal like ATen
   const float inv_h = 1.0f / (float)(H - 1 > 1 ? H - 1 : 1);
-  dim3 grid((unsigned)(((long long)H * W + kThreads - 1) / kThreads), B);
+  // persistent CTAs: one wave of (4 CTAs x 148 SMs) / B per batch item, or fewer when the frame is small
+  const long long n_tiles = ((long long)H * W + kThreads - 1) / kThreads;
+  long long per_b = (148LL * 4 + B - 1) / B;
+  if (per_b > n_tiles) per_b = n_tiles;
+  dim3 grid((unsigned)per_b, B);
   const size_t smem = 2 * K * 5 * sizeof(int);
   const BoxFinalize fd = fin_direct ? *fin_direct : fin_warp;
 #define RMNET_LAUNCH_FB(O, D)                                                                                              \

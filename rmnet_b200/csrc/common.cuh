@@ -246,6 +246,7 @@ struct SchedTable {
   int nqt[SCHED_MAX_OBJ];        // query tiles of object o
   int ns[SCHED_MAX_OBJ];         // KV chunks (= partial slots) of object o
   int count[SCHED_MAX_OBJ];      // stored cells of object o (committed + temporary frame)
+  int stable[SCHED_MAX_OBJ];     // cells [0, stable) are not being written by a concurrently running pack kernel
   int ibase[SCHED_MAX_OBJ + 1];  // first item of object o
 };
 // ceil(a / b) for 0 < b, a < 2^20 via one float multiply and a fix-up (a 32-bit integer division costs ~25 instructions)
@@ -275,8 +276,10 @@ __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict
         const int base = bank_meta[o * 8 + META_CELLS_C];
         const int r = rect_cells(__ldg(reinterpret_cast<const int4 *>(temp_rects) + o));
         count = base + (base + r > cap ? 0 : r);  // bank_pack_kernel drops a frame that would overflow the bank
+        T.stable[o] = base;
       } else {
         count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
+        T.stable[o] = count;
       }
       nt = (count + KV_TILE - 1) / KV_TILE;
       nqt = (rect_cells(qr) + UMMA_QT - 1) / UMMA_QT;

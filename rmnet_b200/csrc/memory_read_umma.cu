@@ -234,9 +234,15 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tstamp && threadIdx.x == 32) tstamp[11] = clock64();
-  pdl_wait();
-  pdl_trigger();
-  if (warp == 3 && !temp_rects) sched_build(sched, bank_meta, q_rects, nullptr, cap, n_obj, h, w, (int)gridDim.x);
+  // Chained launch with an early schedule (temp_rects): only the threads that touch the pack kernel's output wait --
+  // the TMA producers right before their first tile that reaches into the temporary frame, the softmax warpgroup before
+  // it reads the packed query keys; tiles of the committed frames stream in while the pack kernel is still running.
+  // Otherwise (standalone launch, or a commit in the chain) everybody waits here and the schedule is built afterwards.
+  const bool early = temp_rects != nullptr;
+  if (!early) {
+    pdl_wait();
+    if (warp == 3) sched_build(sched, bank_meta, q_rects, nullptr, cap, n_obj, h, w, (int)gridDim.x);
+  }
   if (tstamp && threadIdx.x == 96) tstamp[9] = clock64();
   tc_fence_before();
   __syncthreads();
@@ -255,9 +261,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     // ================= key-tile TMA producer =================
     if (lane == 0) {
       int kt = 0;  // key tiles issued by this CTA so far (ring position / parity run across pieces)
+      bool waited = !early;
       while (iter.next(pc)) {
         for (int it = 0; it < pc.n_it; ++it, ++kt) {
           const int s = kt % KST;
+          if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->k_empty[s]), ((kt / KST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->k_full[s]);
           mbar_expect_tx(full, use_lo ? K_STAGE_BYTES : K_PLANE_BYTES);
@@ -276,9 +284,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     // ================= value-tile TMA producer =================
     if (lane == 0) {
       int vt = 0;
+      bool waited = !early;
       while (iter.next(pc)) {
         for (int it = 0; it < pc.n_it; ++it, ++vt) {
           const int s = vt % VST;
+          if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->v_empty[s]), ((vt / VST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->v_full[s]);
           mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
@@ -364,6 +374,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
     int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
     bool first_piece = true;
+    if (early) pdl_wait();  // the packed query keys (and, through the barriers, everything downstream) need the pack kernel
+    pdl_trigger();          // after the wait: the merge kernel's pre-wait part relies on the bank being final
     // this row's 128 query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's
     // query role in the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that
     // each of the loads below is one coalesced 512 B access per warp
@@ -593,22 +605,42 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
                             int n_splits, const ReadWorkspace &W, const int *temp_rects, bool pdl, cudaStream_t st) {
   RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
   RMNET_CHECK_ARG(n_obj <= SCHED_MAX_OBJ, "tcgen05 path supports at most %d objects per call", (int)SCHED_MAX_OBJ);
-  CUtensorMap mkh, mkl, mvh, mvl;
-  const uint64_t cap = bank.cap, ns = bank.n_slots;
-  int rc;
-  // keys  [slot][cell][128 ch] : box 64 ch x 64 cells (128 B rows)      values [slot][512 ch][cell] : box 64 cells x 256 ch
-  if ((rc = make_map(&mkh, bank.khi, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
-  if ((rc = make_map(&mkl, bank.klo, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
-  if ((rc = make_map(&mvh, bank.vhi, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
-  if ((rc = make_map(&mvl, bank.vlo, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
+  // The four tensor maps depend only on the bank (base pointers, capacity, slots): encode once per bank and thread.
+  struct MapCache { const void *khi; int cap, n_slots; CUtensorMap m[4]; };
+  static thread_local MapCache cache[4] = {};
+  static thread_local int cache_next = 0;
+  const MapCache *mc = nullptr;
+  for (int i = 0; i < 4; ++i)
+    if (cache[i].khi == bank.khi && cache[i].cap == bank.cap && cache[i].n_slots == bank.n_slots) mc = &cache[i];
+  if (!mc) {
+    MapCache &c = cache[cache_next];
+    cache_next = (cache_next + 1) & 3;
+    c.khi = nullptr;
+    const uint64_t cap = bank.cap, ns = bank.n_slots;
+    int rc;
+    // keys  [slot][cell][128 ch] : box 64 ch x 64 cells (128 B rows)      values [slot][512 ch][cell] : box 64 cells x 256 ch
+    if ((rc = make_map(&c.m[0], bank.khi, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
+    if ((rc = make_map(&c.m[1], bank.klo, RMNET_CK, cap, ns, RMNET_CK * 2, cap * RMNET_CK * 2, 64, MT))) return rc;
+    if ((rc = make_map(&c.m[2], bank.vhi, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
+    if ((rc = make_map(&c.m[3], bank.vlo, cap, RMNET_CV, ns, cap * 2, cap * RMNET_CV * 2, MT, CVH))) return rc;
+    c.khi = bank.khi; c.cap = bank.cap; c.n_slots = bank.n_slots;
+    mc = &c;
+  }
+  const CUtensorMap &mkh = mc->m[0], &mkl = mc->m[1], &mvh = mc->m[2], &mvl = mc->m[3];
   const int n_sms = umma_grid_size();
   dim3 grid(n_sms);
   (void)n_splits;
   const bool lo = precision == RMNET_PREC_SPLIT3;
 #define RMNET_LAUNCH_UMMA(F, L)                                                                                          \
   do {                                                                                                                   \
-    RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                    (int)SMEM_BYTES));                                                                   \
+    static bool attr_set[64] = {};                                                                                       \
+    int dev_ = 0;                                                                                                        \
+    RMNET_CUDA(cudaGetDevice(&dev_));                                                                                    \
+    if (dev_ < 0 || dev_ >= 64 || !attr_set[dev_]) {                                                                     \
+      RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                      (int)SMEM_BYTES));                                                                 \
+      if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                                 \
+    }                                                                                                                    \
     RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
                              bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
                              temp_rects, bank.cap, g_dbg));                                                              \

@@ -90,6 +90,10 @@ class RegionalMemory:
         self.k_scan = 0 if scan_all_channels else self.n + 1
         self.bank = ops.MemoryBank(self.n, self.h, self.w, max_frames, device, elem_format)
         self._boxes = None
+        # region-kernel workspace of step(): zero-filled once, left zeroed by every launch (self-cleaning); owned by the
+        # clip (not by the stream) so that a captured step and an eager step share it
+        with torch.cuda.device(self.bank.device):
+            self._box_ws = torch.zeros(4096, dtype=torch.uint8, device=self.bank.device)
 
     def memorize(self, k4, v4, masks, commit):
         """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks [1,K,H,W]: the UNPADDED soft
@@ -128,7 +132,7 @@ class RegionalMemory:
             out = torch.empty((self.n, 1024, self.h, self.w), dtype=torch.float32, device=dev)
         if torch.cuda.current_device() != dev.index:
             torch.cuda.set_device(dev)
-        ws = ops._zero_ws(dev, 4096)
+        ws = self._box_ws
         ops.check(ops.lib().rmnet_frame_step(
             bank.ptr, bank.nbytes, bank.n_slots, bank.cap, prev_mask.data_ptr(), flow.data_ptr(), K, H, W,
             ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, self.k_scan, k4.data_ptr(), v4.data_ptr(),
@@ -141,6 +145,53 @@ class RegionalMemory:
         else:
             bank.has_temp = True
         return out, self._boxes[0:1], self._boxes[2:3]
+
+    def capture_step(self, k4, v4, prev_mask, flow, k4q, v4q, commit, out=None):
+        """step() as a replayable CUDA graph over static input tensors: see CapturedStep."""
+        return CapturedStep(self, k4, v4, prev_mask, flow, k4q, v4q, commit, out)
+
+
+class CapturedStep:
+    """RegionalMemory.step captured once into a CUDA graph (the four chained kernels with their programmatic-dependency
+    edges) and replayed with ONE launch per frame: the per-frame host cost drops from four kernel launches plus the
+    Python / ctypes plumbing to a cudaGraphLaunch.  The input tensors given to capture() are static: write the next
+    frame's data into them (copy_ or let the producing conv write there), then call replay().
+
+        cs = rm.capture_step(k4, v4, prev_mask, flow, k4q, v4q, commit=False)
+        ...fill the static inputs...; m4, prev_bbox, curr_bbox = cs.replay()
+    """
+
+    def __init__(self, rm, k4, v4, prev_mask, flow, k4q, v4q, commit, out=None):
+        self.rm, self.commit = rm, bool(commit)
+        self.inputs = (k4, v4, prev_mask, flow, k4q, v4q)
+        dev = rm.bank.device
+        if out is None:
+            out = torch.empty((rm.n, 1024, rm.h, rm.w), dtype=torch.float32, device=dev)
+        self.out = out
+        # warm-up on a side stream (allocates the box buffer, sets kernel attributes); always without commit: it only
+        # rewrites the temporary frame, exactly what the first replay will do again
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            rm.step(k4, v4, prev_mask, flow, k4q, v4q, commit=False, out=out)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        state = (rm.bank.frames_committed, rm.bank.has_temp)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _, self.prev_bbox, self.curr_bbox = rm.step(k4, v4, prev_mask, flow, k4q, v4q, commit=self.commit, out=out)
+        rm.bank.frames_committed, rm.bank.has_temp = state   # capture enqueued nothing: undo its host bookkeeping
+
+    def replay(self):
+        bank = self.rm.bank
+        if bank.frames_committed + 1 > bank.max_frames:
+            raise RuntimeError(f"memory bank full: {bank.frames_committed} committed frames, capacity {bank.max_frames}")
+        self.graph.replay()
+        if self.commit:
+            bank.frames_committed += 1
+            bank.has_temp = False
+        else:
+            bank.has_temp = True
+        return self.out, self.prev_bbox, self.curr_bbox
 
 
 def install(models_rmnet_module):

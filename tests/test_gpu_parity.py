@@ -478,6 +478,29 @@ def test_step_equals_memorize_then_read():
     np.testing.assert_array_equal(a.bank.stats(), b.bank.stats())
 
 
+def test_captured_step_replays_like_eager_steps():
+    """RegionalMemory.capture_step: the PDL-chained step as a CUDA graph over static inputs == eager step() on the same
+    sequence of frames (non-commit graph and commit graph, as the reference loop alternates them, models/rmnet.py:424)."""
+    n, T, H, W = 2, 4, 240, 432
+    s = _regional_setup(83, n, T, H, W)
+    eager = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV)
+    graph = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV)
+    st = dict(k4=cu(s["mk"][:, :, 0]), v4=cu(s["mv"][:, :, 0]), mask=cu(s["masks"][0][None]), flow=cu(s["flow"][None]),
+              qk=cu(s["qk"]), qv=cu(s["qv"]))
+    args = (st["k4"], st["v4"], st["mask"], st["flow"], st["qk"], st["qv"])
+    cs = {c: graph.capture_step(*args, commit=c) for c in (False, True)}
+    for t, commit in ((0, True), (1, False), (1, True), (2, False), (3, True)):
+        k4, v4, mask = cu(s["mk"][:, :, t]), cu(s["mv"][:, :, t]), cu(s["masks"][t][None])
+        m1, bb1, cb1 = eager.step(k4, v4, mask, st["flow"], st["qk"], st["qv"], commit=commit)
+        st["k4"].copy_(k4); st["v4"].copy_(v4); st["mask"].copy_(mask)
+        m2, bb2, cb2 = cs[commit].replay()
+        np.testing.assert_array_equal(bb1.cpu().numpy(), bb2.cpu().numpy())
+        np.testing.assert_array_equal(cb1.cpu().numpy(), cb2.cpu().numpy())
+        assert (m1 - m2).abs().max().item() <= 1e-6
+    np.testing.assert_array_equal(eager.bank.stats(), graph.bank.stats())
+    assert eager.bank.frames_committed == graph.bank.frames_committed == 3
+
+
 @pytest.mark.parametrize("impl_name,impl", IMPLS, ids=[i[0] for i in IMPLS])
 def test_full_size_properties_480p_T20(impl_name, impl):
     """BASELINE config-3 frame shape (480x864, 5 objects, T=20): size-independent properties instead of the oracle.
