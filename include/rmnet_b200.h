@@ -209,6 +209,28 @@ RMNET_API int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int c
                                void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * The per-frame tail of RMNet.segment / RMNet.forward after the decoder, in ONE pass (batch 1):
+ *   ps = F.softmax(decoder_logits, dim=1)[:, 1]                        (models/rmnet.py:368-370)
+ *   logit = soft_aggregation(ps, K, n_obj)                             (:289-302, :373)
+ *   un-pad by the pad_divide_by amounts                                (:376-380)
+ *   whole-channel overrides of the frame loop                          (:436-448)
+ *   est_mask = F.softmax(logit, dim=1)                                 (:450)
+ *   dec_logits [n_obj,2,H+pad_t+pad_b,W+pad_l+pad_r] f32 (the decoder output);
+ *   channel_mode_host [K] ints (HOST array, read at call time; NULL = all RMNET_CH_KEEP):
+ *     RMNET_CH_KEEP   the soft-aggregation logit,
+ *     RMNET_CH_ABSENT logit := -16.1181               (j <= n_max_objects not in existing_objects, :445-448),
+ *     RMNET_CH_NEW    logit := new_mask[j] * 32.0605 - 16.1181   (object first annotated in this frame, :438-442);
+ *   new_mask [K,H,W] i32 = masks[i,t] (only read for RMNET_CH_NEW channels, may be NULL otherwise);
+ *   logit_out [K,H,W] f32 nullable (the return value of segment() after the overrides); est_mask [K,H,W] f32.
+ * ------------------------------------------------------------------------------------------- */
+#define RMNET_CH_KEEP 0
+#define RMNET_CH_ABSENT 1
+#define RMNET_CH_NEW 2
+RMNET_API int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, int K, int H, int W, int pad_l, int pad_r,
+                                          int pad_t, int pad_b, const int *channel_mode_host, const int *new_mask,
+                                          float *logit_out, float *est_mask, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Literal MemoryReader.forward(m_key, m_val, q_key, q_val) -> mem_val   (models/rmnet.py:147-165)
  *   m_key [n,128,T,h,w], m_val [n,512,T,h,w], q_key [n,128,h,w], q_val [n,512,h,w] (contiguous f32)
  *   mem_val [n,1024,h,w].  Region-agnostic (dense): packs the inputs into a scratch bank inside

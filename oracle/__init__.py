@@ -14,8 +14,11 @@ Parity pin status (the reference's own tests hold NO golden vector for this path
     produced by importing the reference's Python (models/rmnet.py) in the build container
     (tests/golden/make_golden.py, committed next to the vectors).
 
+  * ``mask_epilogue``        -- pinned against golden vectors produced by the reference's own
+    ``RMNet.soft_aggregation`` + the torch ops of models/rmnet.py:368-370, :436-450.
+
 Files: ``rmnet_oracle.c`` (plain C: integer / byte-exact parts), ``memory_read.py`` (numpy:
-the BLAS-backed floating-point reader).
+the BLAS-backed floating-point reader), ``mask_epilogue.py`` (numpy: the post-decoder tail).
 """
 import ctypes
 import os
@@ -160,3 +163,4 @@ def memory_read_f64(m_key, m_val, q_key, q_val, want_p=False):
 
 from .memory_read import (memory_read, regional_mask_memory, regional_mask_query,  # noqa: E402,F401
                           regional_memory_read)
+from .mask_epilogue import CH_ABSENT, CH_KEEP, CH_NEW, mask_epilogue  # noqa: E402,F401

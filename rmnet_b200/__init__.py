@@ -8,4 +8,4 @@ from ._lib import (ELEM_BF16, ELEM_FP16, RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET
                    RMNET_PREC_SPLIT3, build, lib)
 from .modules import (MemoryReader, RegionalAttentionMapGenerator, RegionalAttentionMapGeneratorFunction,  # noqa: F401
                       RegionalMemory, get_att_map, install, warp)
-from .ops import MemoryBank, update_optical_flow  # noqa: F401
+from .ops import MemoryBank, mask_epilogue, update_optical_flow  # noqa: F401

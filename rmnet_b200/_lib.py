@@ -15,6 +15,7 @@ RMNET_PREC_SPLIT3, RMNET_PREC_SINGLE = 0, 1
 RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET_IMPL_UMMA = 0, 1, 2
 ELEM_BF16, ELEM_FP16 = 0, 1
 SAMPLER_CUDNN, SAMPLER_ATEN = 0, 1
+CH_KEEP, CH_ABSENT, CH_NEW = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None
@@ -51,6 +52,8 @@ PROTOTYPES = {
     "rmnet_frame_step": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
+    "rmnet_mask_epilogue_forward": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p]),
     "rmnet_memory_reader_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_memory_reader_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

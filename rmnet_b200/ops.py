@@ -163,6 +163,39 @@ def cell_rects(bboxes, pad_l, pad_t, h, w, skip_channel0_every=0):
     return rects
 
 
+def mask_epilogue(dec_logits, K, frame_hw, channel_modes=None, new_mask=None, want_logit=True):
+    """The tail of RMNet.segment / RMNet.forward after the decoder (models/rmnet.py:368-380, :289-302, :436-450) in one
+    launch.  dec_logits [n,2,Hp,Wp] (decoder output on the padded frame), frame_hw = (H, W) of the unpadded frame,
+    channel_modes: sequence of K ints (CH_KEEP / CH_ABSENT / CH_NEW) or None, new_mask [K,H,W] int32 (masks[i,t]) when a
+    channel is CH_NEW.  -> (logit [1,K,H,W] or None, est_mask [1,K,H,W])"""
+    import ctypes
+    _require(dec_logits, "dec_logits")
+    n, two, Hp, Wp = dec_logits.shape
+    H, W = frame_hw
+    lw, uw, lh, uh = pad_amounts(H, W)
+    if two != 2 or (Hp, Wp) != (H + lh + uh, W + lw + uw):
+        raise RuntimeError(f"dec_logits must be [n,2,{H + lh + uh},{W + lw + uw}]")
+    if new_mask is not None:
+        _require(new_mask, "new_mask", torch.int32)
+        if tuple(new_mask.shape[-3:]) != (K, H, W):
+            raise RuntimeError(f"new_mask must be [{K},{H},{W}]")
+    modes = None
+    if channel_modes is not None:
+        if len(channel_modes) != K:
+            raise RuntimeError("channel_modes must have K entries")
+        modes = (ctypes.c_int * K)(*[int(m) for m in channel_modes])
+    dev = dec_logits.device
+    with torch.cuda.device(dev):
+        logit = torch.empty((1, K, H, W), dtype=torch.float32, device=dev) if want_logit else None
+        est = torch.empty((1, K, H, W), dtype=torch.float32, device=dev)
+        check(lib().rmnet_mask_epilogue_forward(dec_logits.data_ptr(), n, K, H, W, lw, uw, lh, uh,
+                                                ctypes.cast(modes, ctypes.c_void_p) if modes is not None else None,
+                                                new_mask.data_ptr() if new_mask is not None else None,
+                                                logit.data_ptr() if want_logit else None, est.data_ptr(), _stream(dev)),
+              "mask_epilogue_forward")
+    return logit, est
+
+
 def pad_amounts(h, w, d=16):
     """utils/helpers.py:105-119 pad_divide_by -> (lw, uw, lh, uh)."""
     new_h = h + d - h % d if h % d > 0 else h

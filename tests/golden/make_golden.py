@@ -126,7 +126,41 @@ def golden_flow_affine():
     np.savez_compressed(os.path.join(HERE, "flow_affine.npz"), n_cases=len(cases), **out)
 
 
+def golden_mask_epilogue():
+    """The tail after the decoder: models/rmnet.py:368-370 (2-class softmax), the reference's own soft_aggregation
+    (:289-302), the un-pad (:376-380), the channel overrides (:436-448, restated with the same torch expressions: they
+    are inline in RMNet.forward) and the final softmax (:450)."""
+    out = {}
+    #        seed  n  K   H    W   modes (0 keep, 1 absent, 2 new)
+    cases = [(51, 2, 4, 40, 56, None), (52, 3, 11, 33, 47, [0, 0, 0, 2, 1] + [0] * 6), (53, 5, 11, 48, 70, [0, 1, 0, 0, 2, 0] + [0] * 5)]
+    for i, (seed, n, K, H, W, modes) in enumerate(cases):
+        rng = np.random.default_rng(seed)
+        x = synth.decoder_logits(rng, n, H, W)
+        new_mask = (synth.onehot(synth.rect_label_map(rng, K - 1, H, W), K)).astype(np.int32)
+        logits = torch.from_numpy(x)
+        ps = F.softmax(logits, dim=1)[:, 1]                                     # :368-370
+        logit = RMNet.soft_aggregation(None, ps, K, [n])                        # :373 -> :289-302 (reference code)
+        (_,), pad = ref_helpers.pad_divide_by([torch.zeros(1, 1, H, W)], 16, (H, W))
+        if pad[2] + pad[3] > 0:
+            logit = logit[:, :, pad[2]:-pad[3], :]                              # :376-377
+        if pad[0] + pad[1] > 0:
+            logit = logit[:, :, :, pad[0]:-pad[1]]                              # :379-380
+        logit = logit.clone()
+        masks_t = torch.from_numpy(new_mask)
+        for j in range(K):
+            if modes is not None and modes[j] == 2:
+                logit[0, j] = masks_t[j].float() * 32.0605 - 16.1181            # :442
+            if modes is not None and modes[j] == 1:
+                logit[0, j] = -16.1181                                          # :448
+        est = F.softmax(logit, dim=1)                                           # :450
+        out.update({f"c{i}_seed": seed, f"c{i}_n": n, f"c{i}_K": K, f"c{i}_H": H, f"c{i}_W": W,
+                    f"c{i}_modes": np.array(modes if modes is not None else [0] * K), f"c{i}_insum": csum(x, new_mask),
+                    f"c{i}_logit": logit.numpy(), f"c{i}_est": est.numpy()})
+    np.savez_compressed(os.path.join(HERE, "mask_epilogue.npz"), n_cases=len(cases), **out)
+
+
 if __name__ == "__main__":
+    golden_mask_epilogue()
     golden_memory_read()
     golden_regional_read()
     golden_warp()

@@ -71,3 +71,35 @@ def affine_pair(rng):
                       [s * np.sin(a), s * np.cos(a), rng.uniform(-20, 20)]], np.float32)
         ms.append(m)
     return ms
+
+
+def decoder_logits(rng, n_obj, H, W, sharp=6.0):
+    """Decoder output [n,2,Hp,Wp] on the padded frame: object o is likely inside its rectangle, noise elsewhere;
+    a band of exact ties and a band of saturated pixels exercise the clamp (models/rmnet.py:300)."""
+    Hp, Wp = (H + 15) // 16 * 16, (W + 15) // 16 * 16
+    x = rng.standard_normal((n_obj, 2, Hp, Wp)).astype(np.float32)
+    lab = rect_label_map(rng, n_obj, Hp, Wp)
+    for o in range(n_obj):
+        x[o, 1] += sharp * (lab == o + 1)
+        x[o, 0] += sharp * (lab != o + 1)
+    x[:, :, :2, :] = 0.0                 # ties: ps = 0.5 exactly
+    x[:, 1, 2:4, :] += 40.0              # saturated foreground: ps -> 1, clamped
+    x[:, 0, 4:6, :] += 40.0              # saturated background: ps -> 0, clamped
+    return x
+
+
+def epilogue_logit_tolerance(x, K, H, W, base=1e-3, c=8.0):
+    """Per-element bound for comparing two float32 evaluations of models/rmnet.py:289-302 on decoder logits x [n,2,Hp,Wp].
+    log(em / (1 - em)) cancels catastrophically where an object is saturated: one float32 ulp of ps moves 1 - ps by a
+    relative 2^-24 / (1 - ps), and the background product collects that from every object.  Where no object is
+    saturated the bound is `base` (north_star's 1e-3); elsewhere it grows with the amplification that ANY float32
+    implementation of the reference's formula is subject to (torch CPU vs torch CUDA differ by as much)."""
+    x = np.asarray(x, np.float64)
+    n, _, Hp, Wp = x.shape
+    lh, lw = (Hp - H) // 2, (Wp - W) // 2
+    ps = 1.0 / (1.0 + np.exp(x[:, 0] - x[:, 1]))
+    amp = 2.0 ** -24 / np.maximum(1.0 - ps, 2.0 ** -24)
+    tol = np.full((K, Hp, Wp), base)
+    tol[0] += c * amp.sum(0)
+    tol[1:n + 1] += c * amp
+    return tol[None, :, lh:lh + H, lw:lw + W]

@@ -478,6 +478,75 @@ def test_step_equals_memorize_then_read():
     np.testing.assert_array_equal(a.bank.stats(), b.bank.stats())
 
 
+def _torch_mask_epilogue(x, K, H, W, modes, new_mask):
+    """models/rmnet.py:368-380, :289-302, :436-450 with torch's own CUDA ops (what the reference runs on this GPU)."""
+    import torch.nn.functional as F
+    n = x.shape[0]
+    ps = F.softmax(x, dim=1)[:, 1]
+    em = torch.zeros(1, K, *ps.shape[1:], device=x.device)
+    em[0, 0] = torch.prod(1 - ps, dim=0)
+    em[0, 1:n + 1] = ps
+    em = torch.clamp(em, 1e-7, 1 - 1e-7)
+    logit = torch.log((em / (1 - em)))
+    lw, uw, lh, uh = oracle.pad_amounts(H, W)
+    logit = logit[:, :, lh:lh + H, lw:lw + W].clone()
+    for j in range(K):
+        if modes[j] == oracle.CH_NEW:
+            logit[0, j] = new_mask[j].float() * 32.0605 - 16.1181
+        if modes[j] == oracle.CH_ABSENT:
+            logit[0, j] = -16.1181
+    return logit, F.softmax(logit, dim=1)
+
+
+def test_mask_epilogue_vs_golden_oracle_and_torch_cuda(golden_dir):
+    """rmnet_mask_epilogue_forward vs (a) the reference golden vectors (torch CPU), (b) the float32 oracle, (c) torch's
+    own CUDA ops on this GPU.  Bounds: 1e-5 on est_mask; 1e-3 on the logit map (north_star) where the reference's formula
+    is well conditioned and synth.epilogue_logit_tolerance elsewhere; override channels bit-exact."""
+    g = np.load(os.path.join(golden_dir, "mask_epilogue.npz"))
+    for i in range(int(g["n_cases"])):
+        seed, n, K, H, W = (int(g[f"c{i}_{k}"]) for k in ("seed", "n", "K", "H", "W"))
+        modes = [int(m) for m in g[f"c{i}_modes"]]
+        rng = np.random.default_rng(seed)
+        x = synth.decoder_logits(rng, n, H, W)
+        new_mask = synth.onehot(synth.rect_label_map(rng, K - 1, H, W), K).astype(np.int32)
+        tol = synth.epilogue_logit_tolerance(x, K, H, W)
+        logit, est = ops.mask_epilogue(cu(x), K, (H, W), modes, cu(new_mask))
+        lg, es = logit.cpu().numpy(), est.cpu().numpy()
+        assert (np.abs(lg - g[f"c{i}_logit"]) <= tol).all() and np.abs(es - g[f"c{i}_est"]).max() <= 1e-5
+        lo, eo = oracle.mask_epilogue(x, K, (H, W), modes, new_mask)
+        assert (np.abs(lg - lo) <= tol).all() and np.abs(es - eo).max() <= 1e-5
+        lt, et = _torch_mask_epilogue(cu(x), K, H, W, modes, cu(new_mask))
+        dl, de = (logit - lt).abs().max().item(), (est - et).abs().max().item()
+        exact = (logit == lt).float().mean().item()
+        ref_spread = np.abs(lt.cpu().numpy() - g[f"c{i}_logit"]).max()   # torch CUDA vs torch CPU: the reference against itself
+        print(f"mask_epilogue case {i}: vs torch CUDA max|dlogit| {dl:.2e} max|dest| {de:.2e} bit-exact share {exact:.4f}; "
+              f"torch CUDA vs torch CPU max|dlogit| {ref_spread:.2e}")
+        assert (np.abs(lg - lt.cpu().numpy()) <= tol).all() and de <= 1e-5
+        for j, m in enumerate(modes):
+            if m != oracle.CH_KEEP:
+                assert torch.equal(logit[0, j], lt[0, j])
+        _, est2 = ops.mask_epilogue(cu(x), K, (H, W), modes, cu(new_mask), want_logit=False)
+        assert torch.equal(est, est2)
+
+
+def test_mask_epilogue_full_size_properties():
+    """480x854 (padded 480x864), 5 objects, K = 11: est_mask sums to 1 over channels, absent channels carry the constant,
+    channels above n equal the clamp floor, and the result matches torch's CUDA ops within the bounds."""
+    n, K, H, W = 5, 11, 480, 854
+    rng = np.random.default_rng(97)
+    x = synth.decoder_logits(rng, n, H, W)
+    modes = [0] * K
+    modes[2] = oracle.CH_ABSENT
+    logit, est = ops.mask_epilogue(cu(x), K, (H, W), modes, None)
+    assert (est.sum(1) - 1).abs().max().item() <= 1e-6
+    assert (logit[0, 2] == -16.1181).all()
+    floor = torch.log(torch.tensor(1e-7) / (1 - torch.tensor(1e-7))).item()
+    assert (logit[0, n + 1:] == floor).all()
+    lt, et = _torch_mask_epilogue(cu(x), K, H, W, modes, None)
+    tol = synth.epilogue_logit_tolerance(x, K, H, W)
+    assert (np.abs((logit - lt).cpu().numpy()) <= tol).all() and (est - et).abs().max().item() <= 1e-5
+
+
 def test_captured_step_replays_like_eager_steps():
     """RegionalMemory.capture_step: the PDL-chained step as a CUDA graph over static inputs == eager step() on the same
     sequence of frames (non-commit graph and commit graph, as the reference loop alternates them, models/rmnet.py:424)."""

@@ -149,3 +149,30 @@ def test_generator_semantics_edge_cases():
         ref = np.zeros((H, W), np.float32)
         ref[y0:y1 + 1, x0:x1 + 1] = 1
         np.testing.assert_array_equal(att[0, i], ref)
+
+
+def test_mask_epilogue_matches_reference_golden(golden_dir):
+    """oracle.mask_epilogue vs the reference's soft_aggregation + torch ops (models/rmnet.py:368-380, :289-302, :436-450).
+    est_mask (what the frame loop stores, :450) is held to 1e-5; the logit map to 1e-3 (north_star) wherever the
+    reference's own formula is well conditioned, see synth.epilogue_logit_tolerance for the saturated pixels."""
+    g = _load(golden_dir, "mask_epilogue.npz")
+    for i in range(int(g["n_cases"])):
+        seed, n, K, H, W = (int(g[f"c{i}_{k}"]) for k in ("seed", "n", "K", "H", "W"))
+        modes = [int(m) for m in g[f"c{i}_modes"]]
+        rng = np.random.default_rng(seed)
+        x = synth.decoder_logits(rng, n, H, W)
+        new_mask = synth.onehot(synth.rect_label_map(rng, K - 1, H, W), K).astype(np.int32)
+        np.testing.assert_allclose(_csum(x, new_mask), g[f"c{i}_insum"], rtol=1e-12)
+        tol = synth.epilogue_logit_tolerance(x, K, H, W)
+        assert (tol <= 1.1e-3).mean() > 0.25             # a good share of the pixels is held to (essentially) the plain 1e-3
+        logit, est = oracle.mask_epilogue(x, K, (H, W), modes, new_mask)
+        assert logit.shape == (1, K, H, W) and est.shape == (1, K, H, W)
+        assert (np.abs(logit - g[f"c{i}_logit"]) <= tol).all()
+        assert np.abs(est - g[f"c{i}_est"]).max() <= 1e-5
+        # override channels, the clamp ceiling (15.9424, the reference's own comment at :441) and the floor are exact
+        for j, m in enumerate(modes):
+            if m != oracle.CH_KEEP:
+                np.testing.assert_array_equal(logit[0, j], g[f"c{i}_logit"][0, j])
+        assert np.float32(logit.max()) == g[f"c{i}_logit"].max()
+        if K > n + 1 and modes[n + 1] == oracle.CH_KEEP:
+            assert (logit[0, n + 1] == np.float32(np.log(np.float32(1e-7) / (np.float32(1) - np.float32(1e-7))))).all()
