@@ -235,7 +235,8 @@ RMNET_API int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, in
  *   m_key [n,128,T,h,w], m_val [n,512,T,h,w], q_key [n,128,h,w], q_val [n,512,h,w] (contiguous f32)
  *   mem_val [n,1024,h,w].  Region-agnostic (dense): packs the inputs into a scratch bank inside
  *   `workspace` and runs the same read kernel.  workspace >= rmnet_memory_reader_workspace_bytes().
- *   The reference's second output `p [n,T*h*w,h*w]` is produced only when p != NULL (SIMT kernel).
+ *   The reference's second output `p [n,T*h*w,h*w]` (softmax over the memory axis, :155-157) is produced only when
+ *   p != NULL, by a separate fp32 FFMA kernel over the raw keys; the per-frame path never materialises it.
  * ------------------------------------------------------------------------------------------- */
 RMNET_API size_t rmnet_memory_reader_workspace_bytes(int n, int T, int h, int w);
 RMNET_API int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const float *q_key,

@@ -10,6 +10,7 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
 int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
                  const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st);
 bool umma_supported(int cap_cells);
+int launch_attention_probs(const float *m_key, const float *q_key, int n, int M, int N, float *p, cudaStream_t st);
 
 namespace {
 __global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
@@ -150,7 +151,6 @@ int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const fl
   RMNET_CHECK_ARG(m_key && m_val && q_key && q_val && mem_val && workspace, "null pointer argument");
   RMNET_CHECK_ARG(n > 0 && T > 0 && h > 0 && w > 0, "bad shape");
   RMNET_CHECK_ARG((uintptr_t)workspace % 1024 == 0, "workspace must be 1024-byte aligned");
-  if (p != nullptr) { set_error("materialising p [n,T*h*w,h*w] is not implemented yet; pass p = NULL"); return RMNET_E_UNSUPPORTED; }
   size_t off_rects, off_read; int cap;
   const size_t need = reader_scratch_layout(n, T, h, w, &off_rects, &off_read, &cap);
   if (workspace_bytes < need) { set_error("workspace too small: %zu < %zu", workspace_bytes, need); return RMNET_E_WORKSPACE; }
@@ -170,7 +170,10 @@ int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const fl
                              elem_format, /*commit=*/1, stream);
     if (rc) return rc;
   }
-  return rmnet_bank_memory_read(ws, bank_bytes, n, cap, q_key, q_val, (long long)RMNET_CK * N, rects, n, h, w, elem_format,
-                                precision, impl, RMNET_STAGE_ALL, mem_val, ws + off_read, workspace_bytes - off_read, stream);
+  rc = rmnet_bank_memory_read(ws, bank_bytes, n, cap, q_key, q_val, (long long)RMNET_CK * N, rects, n, h, w, elem_format,
+                              precision, impl, RMNET_STAGE_ALL, mem_val, ws + off_read, workspace_bytes - off_read, stream);
+  if (rc || p == nullptr) return rc;
+  // the reference's second output, on request: fp32 scores from the raw keys (attention_probs.cu)
+  return launch_attention_probs(m_key, q_key, n, T * N, N, p, st);
 }
 }

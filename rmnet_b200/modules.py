@@ -39,18 +39,19 @@ class MemoryReader(torch.nn.Module):
     """models/rmnet.py:143-165.  forward(m_key, m_val, q_key, q_val) -> (mem_val, p).
 
     `p` ([n, T*h*w, h*w], 210 MB per object at 480p / T=20) is never materialised by the fused kernel; the only
-    caller ignores it (`m4, viz = self.memory(...)`, models/rmnet.py:361), so None is returned in its place."""
+    caller ignores it (`m4, viz = self.memory(...)`, models/rmnet.py:361), so by default None is returned in its place.
+    `MemoryReader(return_p=True)` restores the reference's tuple (a separate fp32 kernel writes p)."""
 
-    def __init__(self, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16):
+    def __init__(self, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16, return_p=False):
         super().__init__()
-        self.precision, self.impl, self.elem_format = precision, impl, elem_format
+        self.precision, self.impl, self.elem_format, self.return_p = precision, impl, elem_format, return_p
 
     def forward(self, m_key, m_val, q_key, q_val):
         if any(t.requires_grad for t in (m_key, m_val, q_key, q_val)) and torch.is_grad_enabled():
             raise RuntimeError("rmnet_b200.MemoryReader is inference-only (run under torch.no_grad())")
-        mem_val = ops.memory_reader_forward(m_key.contiguous(), m_val.contiguous(), q_key.contiguous(),
-                                            q_val.contiguous(), self.precision, self.impl, self.elem_format)
-        return mem_val, None
+        res = ops.memory_reader_forward(m_key.contiguous(), m_val.contiguous(), q_key.contiguous(), q_val.contiguous(),
+                                        self.precision, self.impl, self.elem_format, want_p=self.return_p)
+        return res if self.return_p else (res, None)
 
 
 def warp(img0, flow):

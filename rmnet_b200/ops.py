@@ -288,8 +288,9 @@ _reader_ws = {}
 
 
 def memory_reader_forward(m_key, m_val, q_key, q_val, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                          elem_format=ELEM_BF16):
-    """Literal MemoryReader.forward (models/rmnet.py:147-165) -> mem_val [n,1024,h,w] (dense, region-agnostic)."""
+                          elem_format=ELEM_BF16, want_p=False):
+    """Literal MemoryReader.forward (models/rmnet.py:147-165) -> mem_val [n,1024,h,w] (dense, region-agnostic);
+    with want_p also the reference's second output p [n,T*h*w,h*w] -> (mem_val, p)."""
     for t, nm in ((m_key, "m_key"), (m_val, "m_val"), (q_key, "q_key"), (q_val, "q_val")):
         _require(t, nm)
     n, ck, T, h, w = m_key.shape
@@ -305,10 +306,12 @@ def memory_reader_forward(m_key, m_val, q_key, q_val, precision=RMNET_PREC_SPLIT
             _reader_ws[key] = ws
         ptr = ws.data_ptr() + ((-ws.data_ptr()) % 1024)
         out = torch.empty((n, 2 * CV, h, w), dtype=torch.float32, device=dev)
+        p = torch.empty((n, T * h * w, h * w), dtype=torch.float32, device=dev) if want_p else None
         check(lib().rmnet_memory_reader_forward(m_key.data_ptr(), m_val.data_ptr(), q_key.data_ptr(), q_val.data_ptr(),
-                                                n, T, h, w, elem_format, precision, impl, out.data_ptr(), None, ptr,
-                                                ws.numel() - 1024, _stream(dev)), "memory_reader_forward")
-    return out
+                                                n, T, h, w, elem_format, precision, impl, out.data_ptr(),
+                                                p.data_ptr() if want_p else None, ptr, ws.numel() - 1024, _stream(dev)),
+              "memory_reader_forward")
+    return (out, p) if want_p else out
 
 
 def update_optical_flow_cuda(of, m1, m2):

@@ -297,6 +297,27 @@ def test_memory_reader_matches_reference_golden(golden_dir, impl_name, impl):
         np.testing.assert_array_equal(got[:, synth.CV:], ins[3])
 
 
+def test_memory_reader_second_output_p_matches_reference_golden(golden_dir):
+    """MemoryReader(return_p=True): the reference's (mem_val, p) tuple; p = softmax over the memory axis
+    (models/rmnet.py:155-157) against the golden p the reference produced, columns summing to one, and the C1 shape
+    (240x432, T = 3) against the fp64 oracle."""
+    g = np.load(os.path.join(golden_dir, "memory_read.npz"))
+    reader = rmnet_b200.MemoryReader(return_p=True)
+    for i in range(int(g["n_cases"])):
+        a = {k: g[f"c{i}_{k}"] for k in ("seed", "n", "T", "h", "w", "scale", "mem", "p")}
+        ins = synth.memory_read_inputs(int(a["seed"]), int(a["n"]), int(a["T"]), int(a["h"]), int(a["w"]), float(a["scale"]))
+        mem_val, p = reader(*(cu(x) for x in ins))
+        assert tuple(p.shape) == a["p"].shape
+        assert np.abs(p.cpu().numpy() - a["p"]).max() <= 5e-6, f"case {i}"
+        assert (p.sum(1) - 1).abs().max().item() <= 1e-5
+        assert np.abs(mem_val.cpu().numpy()[:, :synth.CV] - a["mem"].reshape(mem_val.shape[0], synth.CV, *mem_val.shape[2:])).max() <= TOL_STRICT
+    n, T, h, w = 1, 3, 15, 27
+    ins = synth.memory_read_inputs(7, n, T, h, w, 0.5)
+    _, p = reader(*(cu(x) for x in ins))
+    _, p_ref = oracle.memory_read(*ins, dtype=np.float64, want_p=True)
+    assert np.abs(p.cpu().numpy() - p_ref).max() <= 5e-6
+
+
 @pytest.mark.parametrize("impl_name,impl", IMPLS, ids=[i[0] for i in IMPLS])
 @pytest.mark.parametrize("shape", [(1, 3, 15, 27, 1.0), (3, 5, 30, 54, 0.5), (2, 2, 7, 9, 2.0), (1, 1, 1, 1, 1.0), (2, 3, 30, 54, 0.25)],
                          ids=["c1_240x432_T3", "c2_480x864_T5", "tiny_ragged", "single_cell", "cond_T3"])
