@@ -293,27 +293,33 @@ __device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict
   // candidates: every chunk length c in [c_min, 64] (two per lane), c_min from the partial-slot bound.
   // 32-bit unsigned arithmetic only: 64-bit integer division is emulated with hundreds of instructions.
   const unsigned c_min = max(1u, ((unsigned)max_nt + READ_MAX_SPLITS - 1) / READ_MAX_SPLITS);
+  // Both candidates of a lane are evaluated in ONE walk over the objects (independent chains: the walk is latency-
+  // bound integer arithmetic, and in a stand-alone launch it sits on the kernel's critical path).
+  const unsigned cand[2] = {(unsigned)lane + 1u, (unsigned)lane + 33u};
+  const float rcp[2] = {__frcp_rn((float)cand[0]), __frcp_rn((float)cand[1])};
+  unsigned items[2] = {0u, 0u}, longest[2] = {0u, 0u};
+#pragma unroll 2
+  for (int o = 0; o < n_obj; ++o) {
+    const unsigned nt = T.nt[o], w2 = 2u * (unsigned)T.nqt[o];
+    if (nt > 0 && w2 > 0) {
+#pragma unroll
+      for (int rep = 0; rep < 2; ++rep) {
+        const unsigned ns = ceil_div_small(nt, cand[rep], rcp[rep]);
+        items[rep] += ns * w2;
+        longest[rep] = max(longest[rep], ceil_div_small(nt, ns, __frcp_rn((float)ns)));  // balanced chunks: the longest actual chunk
+      }
+    }
+  }
   unsigned best = 0xffffffffu, best_c = c_min;
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
-    const unsigned c = lane + 1 + 32 * rep;
-    unsigned cost = 0xffffffffu;
+    const unsigned c = cand[rep];
     if (c >= c_min && c <= MAX_TILES_PER_SPLIT && c <= (unsigned)max(max_nt, 1)) {
-      unsigned items = 0, longest = 0;
-      const float rcp_c = 1.0f / (float)c;
-      for (int o = 0; o < n_obj; ++o) {
-        const unsigned nt = T.nt[o];
-        if (nt > 0 && T.nqt[o] > 0) {
-          const unsigned ns = ceil_div_small(nt, c, rcp_c);
-          items += ns * 2u * (unsigned)T.nqt[o];
-          longest = max(longest, ceil_div_small(nt, ns, 1.0f / (float)ns));  // balanced chunks: the longest actual chunk
-        }
-      }
-      const unsigned rounds = (items + G - 1) / (unsigned)G;
+      const unsigned rounds = (items[rep] + G - 1) / (unsigned)G;
       // makespan estimate in tile units: rounds x (longest chunk + per-item prologue/epilogue ~ 5 tiles); ties -> fewer chunks
-      cost = (rounds * (longest + 5u)) * 128u + (64u - c);
+      const unsigned cost = (rounds * (longest[rep] + 5u)) * 128u + (64u - c);
+      if (cost < best) { best = cost; best_c = c; }
     }
-    if (cost < best) { best = cost; best_c = c; }
   }
   const unsigned bcast = __reduce_min_sync(0xffffffffu, best);
   const unsigned who = __ballot_sync(0xffffffffu, best == bcast);

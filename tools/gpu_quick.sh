@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu.log
-timeout 400 python bench.py --cpu-steps 2 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
+timeout 400 python bench.py --workload c2 --cpu-steps 2 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench c2 rc=$?"
 timeout 400 python bench.py --workload c3 --cpu-steps 1 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; echo "bench c3 rc=$?"
 timeout 300 python tools/step_breakdown.py > gpurun_out/step_breakdown.log 2>&1; echo "breakdown rc=$?"
 timeout 300 python tools/umma_timeline.py > gpurun_out/umma_timeline.log 2>&1; echo "timeline rc=$?"
