@@ -12,7 +12,7 @@ The ResNet-50 encoders / decoder that produce k4/v4 and consume mem_val are the 
 scope: their outputs are synthetic tensors of the right shape.  Metric: frames/sec of this path
 (BASELINE.json `metric`), `value` with inputs resident in HBM, `e2e` through the public API with pinned HOST buffers.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
 """
 import argparse
 import json
@@ -33,6 +33,8 @@ WORKLOADS = {
     "c2": dict(H=480, W=854, n=3, T=5, desc="480x854 (padded 480x864) clip frame, 3 objects, T=5 memory frames, K=11 mask channels"),
     # BASELINE.json configs[2] / north_star target shape: 480p, 5 objects, T=20
     "c3": dict(H=480, W=854, n=5, T=20, desc="480x854 (padded 480x864) clip frame, 5 objects, T=20 memory frames, K=11 mask channels"),
+    # BASELINE.json configs[3]: YouTube-VOS-shaped, 720p, 10 objects, T=40 (long memory); slow to set up, CPU sample = 1 step
+    "c4": dict(H=720, W=1280, n=10, T=40, desc="720x1280 clip frame, 10 objects, T=40 memory frames, K=11 mask channels"),
 }
 K_CH = 11
 METRIC = "480p VOS frames/sec (regional memory-read hot path)"
@@ -255,7 +257,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
 
     n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
-    POOL = 8
+    POOL = 8 if args.workload != "c4" else 3
     pool = make_pool(wl, 1234 + rank, POOL)
     h, w, lw, Wp = pool["h"], pool["w"], pool["lw"], pool["Wp"]
     N = h * w
@@ -486,7 +488,7 @@ def main():
         if rank != 0:
             return
         pool = make_pool(wl, 1234, 4)
-        steps = min(args.steps, 20 if args.workload == "c2" else 8)
+        steps = min(args.steps, {"c2": 20, "c3": 8}.get(args.workload, 1))
         fps, ms, _ = time_cpu(wl, pool, steps, min(args.warmup, 2))
         cores = os.cpu_count()
         print(json.dumps({
@@ -508,7 +510,7 @@ def main():
     if rank == 0:
         line, pool = res
         if world == 1:
-            steps = args.cpu_steps or (20 if args.workload == "c2" else 10)
+            steps = args.cpu_steps or {"c2": 20, "c3": 10}.get(args.workload, 1)
             fps, ms, _ = time_cpu(wl, make_pool(wl, 1234, 4), steps, 1)
             cores = os.cpu_count()
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(), "ms_per_step": ms,

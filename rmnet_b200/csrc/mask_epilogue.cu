@@ -6,8 +6,9 @@
 //   :376-380  un-pad (pad_divide_by amounts)
 //   :436-448  new-object / non-existing-object overrides of whole logit channels
 //   :450      est_masks[:, t] = F.softmax(logit, dim=1)
-// -- about ten elementwise ATen passes over [K,Hp,Wp] in the reference.  HBM-bound: 8*n*Hp*Wp bytes read,
-// 4*K*H*W (+ 4*K*H*W when the logit map is requested) written; one pixel per thread, coalesced along x.
+// -- about ten elementwise ATen passes over [K,Hp,Wp] in the reference.  Algorithmic traffic: 8*n*Hp*Wp bytes read,
+// 4*K*H*W (+ 4*K*H*W when the logit map is requested) written; one pixel per thread, coalesced along x.  In practice
+// the kernel is issue-bound on the IEEE division / logf / expf sequences that bit-exactness needs.
 // The arithmetic mirrors the ATen kernels op for op (separately rounded fp32 steps, libdevice expf / logf, the product
 // over objects in torch.prod's four-accumulator order) so that the logit map agrees with the reference's to the last bit
 // wherever the two libm's agree; the parity tests bound the difference by 1e-3 (north_star) and report the exact share.
@@ -17,9 +18,17 @@ namespace rmnet {
 namespace {
 
 constexpr int kThreads = 256;
-struct ChannelModes { unsigned char m[64]; };
+// per-channel override mode, 2 bits per channel (K <= 64): decoded with shifts, no dynamically indexed parameter array
+struct ChannelModes {
+  unsigned long long bits[2];
+  __host__ __device__ int get(int c) const { return (int)(((c < 32 ? bits[0] : bits[1]) >> (2 * (c & 31))) & 3ull); }
+  __host__ void set(int c, int m) { bits[c >> 5] |= (unsigned long long)m << (2 * (c & 31)); }
+};
 
-template <int KMAX>
+// NOBJ = compile-time bound on n_obj: the channels 0..n_obj (background + real objects) are the only ones with per-pixel
+// transcendental work and live in registers (unrolled); the channels above n_obj are the clamp floor or a whole-channel
+// override -- constants per pixel -- and are walked by a plain runtime loop.  Summation orders are the reference's.
+template <int NOBJ>
 __global__ void __launch_bounds__(kThreads)
 mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int H, int W, int Hp, int Wp, int pad_l, int pad_t,
                      ChannelModes modes, const int *__restrict__ new_mask, float *__restrict__ logit_out,
@@ -32,11 +41,11 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
   const long long plane_p = (long long)Hp * Wp;
   const float lo = (float)1e-7, hi = (float)(1.0 - 1e-7);  // torch.clamp casts its python-float bounds to float32
 
-  float lg[KMAX];
+  float lg[NOBJ + 1];
   // ---- ps of every object (two-class softmax, ATen order: max, exp(x - max), sum c = 0,1, divide), background product
   float acc[4] = {1.f, 1.f, 1.f, 1.f};  // torch.prod over dim 0: four strided accumulators, combined 0..3
 #pragma unroll
-  for (int o = 0; o < KMAX - 1; ++o) {
+  for (int o = 0; o < NOBJ; ++o) {
     if (o < n_obj) {
       const float l0 = __ldg(dec_logits + (long long)(2 * o) * plane_p + jp);
       const float l1 = __ldg(dec_logits + (long long)(2 * o + 1) * plane_p + jp);
@@ -48,19 +57,23 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
     }
   }
   lg[0] = __fmul_rn(__fmul_rn(__fmul_rn(acc[0], acc[1]), acc[2]), acc[3]);
-  // ---- clamp, logit, per-channel overrides.  Channels above n_obj hold em = 0 -> the clamp floor -> one constant logit
-  //      (no division / logarithm per pixel); the kernel is bound by these multi-instruction fp32 functions, not by HBM.
+
+  // value of a channel that needs no per-pixel arithmetic: the clamp floor (em = 0, :293 + :300-301) or an override
   const float floor_logit = logf(__fdiv_rn(lo, __fsub_rn(1.0f, lo)));
+  auto const_channel = [&](int c, int mode) -> float {
+    if (mode == RMNET_CH_ABSENT) return -16.1181f;                                                              // :448
+    if (mode == RMNET_CH_NEW)
+      return __fsub_rn(__fmul_rn((float)__ldg(new_mask + (long long)c * n_pixels + j), 32.0605f), 16.1181f);   // :442
+    return floor_logit;
+  };
+  // ---- pass 1: logits (clamp, log(em / (1 - em)), overrides), their maximum
   float mx = -INFINITY;
 #pragma unroll
-  for (int c = 0; c < KMAX; ++c) {
-    if (c < K) {
-      const int mode = modes.m[c];
+  for (int c = 0; c <= NOBJ; ++c) {
+    if (c <= n_obj) {
+      const int mode = modes.get(c);
       float v;
-      if (mode == RMNET_CH_ABSENT) v = -16.1181f;                                                        // :448
-      else if (mode == RMNET_CH_NEW)
-        v = __fsub_rn(__fmul_rn((float)__ldg(new_mask + (long long)c * n_pixels + j), 32.0605f), 16.1181f);  // :442
-      else if (c > n_obj) v = floor_logit;
+      if (mode != RMNET_CH_KEEP) v = const_channel(c, mode);
       else {
         const float em = fminf(fmaxf(lg[c], lo), hi);
         v = logf(__fdiv_rn(em, __fsub_rn(1.0f, em)));
@@ -70,25 +83,34 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
       mx = fmaxf(mx, v);
     }
   }
-  // ---- channel softmax (:450): exp(x - max) summed c = 0..K-1, then exp(x - max) / sum.  The constant channels share
-  //      one exponential and one quotient (same bits as recomputing them), the sum keeps the reference's order.
+  for (int c = n_obj + 1; c < K; ++c) {
+    const float v = const_channel(c, modes.get(c));
+    if (logit_out) logit_out[(long long)c * n_pixels + j] = v;
+    mx = fmaxf(mx, v);
+  }
+  // ---- pass 2 (:450): exp(x - max) summed c = 0..K-1; the floor channels share one exponential (same bits)
   const float e_floor = expf(__fsub_rn(floor_logit, mx));
   float sum = 0.f;
 #pragma unroll
-  for (int c = 0; c < KMAX; ++c) {
-    if (c < K) {
-      const bool is_floor = c > n_obj && modes.m[c] == RMNET_CH_KEEP;
-      lg[c] = is_floor ? e_floor : expf(__fsub_rn(lg[c], mx));
+  for (int c = 0; c <= NOBJ; ++c) {
+    if (c <= n_obj) {
+      lg[c] = expf(__fsub_rn(lg[c], mx));
       sum = __fadd_rn(sum, lg[c]);
     }
   }
-  const float q_floor = __fdiv_rn(e_floor, sum);
+  for (int c = n_obj + 1; c < K; ++c) {
+    const int mode = modes.get(c);
+    sum = __fadd_rn(sum, mode == RMNET_CH_KEEP ? e_floor : expf(__fsub_rn(const_channel(c, mode), mx)));
+  }
+  // ---- pass 3: exp(x - max) / sum; the floor channels share one quotient
 #pragma unroll
-  for (int c = 0; c < KMAX; ++c) {
-    if (c < K) {
-      const bool is_floor = c > n_obj && modes.m[c] == RMNET_CH_KEEP;
-      est_mask[(long long)c * n_pixels + j] = is_floor ? q_floor : __fdiv_rn(lg[c], sum);
-    }
+  for (int c = 0; c <= NOBJ; ++c)
+    if (c <= n_obj) est_mask[(long long)c * n_pixels + j] = __fdiv_rn(lg[c], sum);
+  const float q_floor = __fdiv_rn(e_floor, sum);
+  for (int c = n_obj + 1; c < K; ++c) {
+    const int mode = modes.get(c);
+    est_mask[(long long)c * n_pixels + j] =
+        mode == RMNET_CH_KEEP ? q_floor : __fdiv_rn(expf(__fsub_rn(const_channel(c, mode), mx)), sum);
   }
 }
 
@@ -111,7 +133,7 @@ int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, int K, int H
     for (int c = 0; c < K; ++c) {
       const int m = channel_mode_host[c];
       RMNET_CHECK_ARG(m == RMNET_CH_KEEP || m == RMNET_CH_ABSENT || m == RMNET_CH_NEW, "bad channel mode %d for channel %d", m, c);
-      modes.m[c] = (unsigned char)m;
+      modes.set(c, m);
       any_new |= m == RMNET_CH_NEW;
     }
   }
@@ -120,12 +142,13 @@ int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, int K, int H
   const long long n_pixels = (long long)H * W;
   dim3 grid((unsigned)((n_pixels + kThreads - 1) / kThreads));
   cudaStream_t st = (cudaStream_t)stream;
-#define RMNET_LAUNCH_EPI(KM)                                                                                                   \
-  mask_epilogue_kernel<KM><<<grid, kThreads, 0, st>>>(dec_logits, n_obj, K, H, W, Hp, Wp, pad_l, pad_t, modes, new_mask, logit_out, \
+#define RMNET_LAUNCH_EPI(NO)                                                                                                   \
+  mask_epilogue_kernel<NO><<<grid, kThreads, 0, st>>>(dec_logits, n_obj, K, H, W, Hp, Wp, pad_l, pad_t, modes, new_mask, logit_out, \
                                                       est_mask)
-  if (K <= 12) RMNET_LAUNCH_EPI(12);
-  else if (K <= 32) RMNET_LAUNCH_EPI(32);
-  else RMNET_LAUNCH_EPI(64);
+  if (n_obj <= 5) RMNET_LAUNCH_EPI(5);         // DAVIS-like clips
+  else if (n_obj <= 11) RMNET_LAUNCH_EPI(11);  // YouTube-VOS-like clips (N_MAX_OBJECTS = 10)
+  else if (n_obj <= 31) RMNET_LAUNCH_EPI(31);
+  else RMNET_LAUNCH_EPI(63);
 #undef RMNET_LAUNCH_EPI
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;

@@ -630,6 +630,58 @@ def test_simt_and_umma_agree_at_full_size():
     assert (a - b).abs().max().item() <= TOL_STRICT
 
 
+def test_c4_shape_regional_and_huge_dense_bank_umma_vs_simt():
+    """BASELINE config 4's frame shape (720x1280 -> 45x80 cells, 10 objects, T = 40): the largest configuration.
+      (a) regional: per-frame random cell rectangles (region fraction ~0.3), 10 objects x 40 frames -- the tcgen05
+          path against the independent fp32 FFMA kernel on the same bank, plus the bank's cell accounting;
+      (b) dense, 2 objects: 2 250 KV tiles per object exceed chain bound x partial slots (64 x 16), so the scheduler
+          falls back to the slot bound (141-tile chains); constant values must still be reproduced."""
+    if not _impl_available(rmnet_b200.RMNET_IMPL_UMMA):
+        pytest.skip("tcgen05 kernel not built")
+    h, w, T = 45, 80, 40
+    g = torch.Generator(device=DEV).manual_seed(5)
+    rng = np.random.default_rng(5)
+
+    def rand_rects(n):
+        r = np.zeros((n, 4), np.int32)
+        for o in range(n):
+            rw_, rh_ = int(rng.integers(w // 3, 3 * w // 4)), int(rng.integers(h // 3, 3 * h // 4))
+            x0, y0 = int(rng.integers(0, w - rw_ + 1)), int(rng.integers(0, h - rh_ + 1))
+            r[o] = (x0, x0 + rw_ - 1, y0, y0 + rh_ - 1)
+        return r
+
+    n = 10
+    bank = ops.MemoryBank(n, h, w, T, DEV)
+    stored = np.zeros(n, np.int64)
+    for t in range(T):
+        r = rand_rects(n)
+        stored += (r[:, 1] - r[:, 0] + 1) * (r[:, 3] - r[:, 2] + 1)
+        bank.memorize(torch.randn((n, synth.CK, h, w), device=DEV, generator=g) * 0.3,
+                      torch.randn((n, synth.CV, h, w), device=DEV, generator=g), cu(r), commit=True)
+    st = bank.stats()
+    np.testing.assert_array_equal(st[:, 0], stored)
+    np.testing.assert_array_equal(st[:, 0] + st[:, 2], np.full(n, T * h * w))
+    qk = torch.randn((synth.CK, h, w), device=DEV, generator=g) * 0.3
+    qv = torch.randn((synth.CV, h, w), device=DEV, generator=g)
+    qr = cu(rand_rects(n))
+    a = bank.read(qk, qv, qr, n, impl=rmnet_b200.RMNET_IMPL_UMMA)
+    b = bank.read(qk, qv, qr, n, impl=rmnet_b200.RMNET_IMPL_SIMT)
+    assert torch.isfinite(a).all()
+    assert (a - b).abs().max().item() <= TOL_STRICT
+    del bank, a, b
+
+    n = 2
+    const = rng.standard_normal(synth.CV).astype(np.float32)
+    vconst = cu(np.broadcast_to(const[None, :, None, None], (n, synth.CV, h, w)).copy())
+    dense = torch.tensor([[0, w - 1, 0, h - 1]] * n, dtype=torch.int32, device=DEV)
+    bank = ops.MemoryBank(n, h, w, T, DEV)
+    for t in range(T):
+        bank.memorize(torch.randn((n, synth.CK, h, w), device=DEV, generator=g) * 0.3, vconst, dense, commit=True)
+    got = bank.read(qk, qv, dense, n, impl=rmnet_b200.RMNET_IMPL_UMMA).cpu().numpy()
+    assert np.abs(got[:, :synth.CV] - const[None, :, None, None]).max() <= 3 * TOL_STRICT   # 141-tile chains: ~2x the bias of 64
+    np.testing.assert_array_equal(got[:, synth.CV:], np.broadcast_to(qv.cpu().numpy(), got[:, synth.CV:].shape))
+
+
 def test_dropin_modules_resolve_like_the_reference_imports():
     """`import reg_att_map_generator` / `import flow_affine_transformation` (extensions/reg_att_map_generator/
     __init__.py:11, utils/data_transforms.py:18) resolve to the drop-ins when rmnet_b200/dropin is on sys.path."""

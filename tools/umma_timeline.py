@@ -17,8 +17,17 @@ for wlname in ("c2", "c3"):
     for _ in range(3): rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
     dbg = torch.zeros(8448 + 148 * 32 + 64, device=dev)
     torch.cuda.synchronize()
+    standalone = len(sys.argv) > 1 and sys.argv[1] == "standalone"
+    if standalone:   # the read kernel launched alone (no PDL chain): what bench.py's roofline times
+        _, rq0 = rmnet_b200.ops.regional_boxes(d["mask"][None], d["flow"][None], padded_frame=False, k_scan=n + 1)
+        rq0 = rq0[0, 1:n + 1].contiguous()
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev); flush.zero_()
+        torch.cuda.synchronize()
     L.rmnet_debug_set_umma_dump(dbg.data_ptr())
-    rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
+    if standalone:
+        rm.bank.read(d["qk"], d["qv"], rq0, n, stages=1)
+    else:
+        rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
     torch.cuda.synchronize()
     L.rmnet_debug_set_umma_dump(None)
     ts = dbg[8448:8448 + 148 * 32].view(torch.int64).view(148, 16).cpu().numpy()
