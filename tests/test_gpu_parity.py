@@ -93,20 +93,8 @@ def test_generator_other_parameters():
 
 def _torch_warp(img0, flow):
     """RMNet.warp restated with the same torch ops on the GPU (models/rmnet.py:252-278): the floating-point reference."""
-    import torch.nn.functional as F
-    B, C, H, W = img0.size()
-    x_axis = torch.arange(0, W).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1)
-    y_axis = torch.arange(0, H).view(-1, 1).repeat(1, W).view(1, 1, H, W).repeat(B, 1, 1, 1)
-    grid = torch.cat((x_axis, y_axis), 1).float().to(img0.device)
-    vgrid = grid + flow
-    vgrid[:, 0, :, :] = 2.0 * vgrid[:, 0, :, :].clone() / max(W - 1, 1) - 1.0
-    vgrid[:, 1, :, :] = 2.0 * vgrid[:, 1, :, :].clone() / max(H - 1, 1) - 1.0
-    vgrid = vgrid.permute(0, 2, 3, 1)
-    img1 = F.grid_sample(img0.clone(), vgrid, align_corners=True)
-    mask = F.grid_sample(torch.ones_like(img0), vgrid, align_corners=True)
-    mask[mask < 0.9999] = 0
-    mask[mask > 0] = 1
-    return img1 * mask, mask
+    from ref_composition import torch_warp
+    return torch_warp(img0, flow)
 
 
 def _warp_cases():
@@ -566,6 +554,35 @@ def test_mask_epilogue_full_size_properties():
     lt, et = _torch_mask_epilogue(cu(x), K, H, W, modes, None)
     tol = synth.epilogue_logit_tolerance(x, K, H, W)
     assert (np.abs((logit - lt).cpu().numpy()) <= tol).all() and (est - et).abs().max().item() <= 1e-5
+
+
+def test_step_matches_the_reference_composition_at_full_size():
+    """RegionalMemory.step against the reference's own composition of the frame step on this GPU (tests/ref_composition.py:
+    torch's CUDA ops for pad / warp / interpolate / bmm / softmax / cat and the UNMODIFIED reference CUDA kernel for both
+    get_att_map calls) at BASELINE config 2's full size (480x854, 3 objects, T = 5, K = 11): bounding boxes bit-exact,
+    mem_val within 2e-4 (measured 2e-6), over three consecutive frames with a commit in between."""
+    gen = _ref_generator()
+    if gen is None:
+        pytest.skip("oracle/_ref/reg_att_map_generator*.so not built (make -C oracle ref)")
+    from ref_composition import ReferenceClip
+    import bench
+    wl = bench.WORKLOADS["c2"]
+    n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
+    pool = bench.make_pool(wl, 4321, 3)
+    fr = [{k: cu(v) for k, v in f.items()} for f in pool["frames"]]
+    ref = ReferenceClip(gen, n, bench.K_CH, H, W)
+    rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T + 1, device=DEV)
+    for t in range(T - 1):
+        ref.commit(fr[t])
+        rm.memorize(fr[t]["k4"], fr[t]["v4"], fr[t]["mask"][None], commit=True)
+    for t, commit in ((T - 1, False), (T, True), (T + 1, False)):
+        cur = fr[t]
+        m_ref, pb_ref, cb_ref = ref.step(cur)
+        m, pb, cb = rm.step(cur["k4"], cur["v4"], cur["mask"][None], cur["flow"][None], cur["qk"], cur["qv"], commit=commit)
+        assert torch.equal(pb, pb_ref) and torch.equal(cb, cb_ref)
+        assert (m - m_ref).abs().max().item() <= TOL_STRICT
+        if commit:
+            ref.commit(cur)
 
 
 def test_captured_step_replays_like_eager_steps():
