@@ -460,6 +460,40 @@ def run_gpu(args, wl, rank, world, local_rank):
     except (OSError, ValueError):
         pass
 
+    # ---- the reference's own composition of the same step on THIS GPU (torch CUDA ops + the unmodified reference CUDA
+    #      kernel from oracle/_ref; tests/ref_composition.py), rank 0 at N = 1 only: the GPU-vs-GPU bar, reported beside
+    #      the CPU baseline.  Skipped (with the reason) when the reference extension was not built.
+    ref_gpu = None
+    if world == 1 and args.workload != "c4":
+        try:
+            import glob
+            so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "reg_att_map_generator*.so"))
+            if not so:
+                raise RuntimeError("oracle/_ref/reg_att_map_generator*.so not built")
+            sys.path.insert(0, os.path.dirname(so[0]))
+            import reg_att_map_generator as ref_gen
+            from ref_composition import ReferenceClip
+            rc = ReferenceClip(ref_gen, n, K_CH, H, W)
+            for t in range(T - 1):
+                rc.commit({k: torch.from_numpy(v).to(dev) for k, v in frames[t].items()})
+            for _ in range(2):
+                rc.step(dframes[0])
+            ts = []
+            for _ in range(5):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); m_ref, _, _ = rc.step(dframes[0]); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            ours0 = step_dev(dframes[0])
+            ref_gpu = {"ms_per_step": float(np.median(ts)), "frames_per_s": 1e3 / float(np.median(ts)),
+                       "max_abs_diff_mem_val": float((ours0 - m_ref).abs().max().item()),
+                       "what": "models/rmnet.py:191-205,:212,:244-248,:252-287,:307,:355-358,:416-426,:147-165 restated with torch's CUDA ops "
+                               "+ the unmodified reference CUDA kernel (oracle/_ref), same inputs, L2 flushed"}
+            del rc, m_ref
+        except Exception as e:
+            ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
+
     # ---- max over ranks, trivial NCCL gather of a result checksum (north_star: "NCCL only for the result gather")
     checksum = float(m4.double().sum().item())
     dev_ms, e2e_s, sums = reduce_over_ranks(dev_ms, e2e_s, checksum, dev, rank, world)
@@ -479,7 +513,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "e2e_mode": "one pinned host staging buffer per frame (mask channels 1..n, flow, k4, v4, q_key, q_val) -> one H2D copy -> "
                                "RegionalMemory.step -> D2H of mem_val every step; copies double-buffered on side streams"},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches, "cuda_graph": graph_info, "roofline": roof, "clocks": clk, "result_checksums": sums,
+        "gpu_launches": launches, "cuda_graph": graph_info, "reference_on_this_gpu": ref_gpu, "roofline": roof, "clocks": clk, "result_checksums": sums,
     }
     return line, pool
 
