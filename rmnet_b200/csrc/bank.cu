@@ -176,18 +176,30 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
   for (int k = 0; k < kPerThread; ++k) x[k] = live ? __ldg(vp + (long long)(cbase + cg + kGroups * k) * v_ch_stride) : 0.f;
 #pragma unroll
   for (int k = 0; k < kPerThread; ++k) {
-    const int c = cbase + cg + kGroups * k;
     if (live) {
+      const int c = cbase + cg + kGroups * k;
       uint16_t hi, lo;
       split16(x[k], FMT, hi, lo);
       bank.vhi[vrow0 + (size_t)c * bank.cap] = hi;
       bank.vlo[vrow0 + (size_t)c * bank.cap] = lo;
     }
-    float sum = x[k];
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
-    if ((threadIdx.x & 31) == 0) atomicAdd(&sm.vsum[c - cbase], sum);  // two warps share a channel
   }
+  // Per-channel sums over the warp's 32 cells by a transpose-reduction: in step s every lane keeps half of its values
+  // and adds the partner's copy of the same half (31 shuffles instead of 32 x 5); lane l ends up with the total of its
+  // l-th channel.  Dead lanes hold zeros.
+  static_assert(kPerThread == 32, "the transpose-reduction below assumes 32 channels per thread");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int sft = 16; sft >= 1; sft >>= 1) {
+    const bool upper = (lane & sft) != 0;
+#pragma unroll
+    for (int j = 0; j < sft; ++j) {
+      const float keep = upper ? x[j + sft] : x[j];
+      const float send = upper ? x[j] : x[j + sft];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, sft);
+    }
+  }
+  atomicAdd(&sm.vsum[cg + kGroups * lane], x[0]);  // the two warps of a channel group meet here
   __syncthreads();
   if (threadIdx.x < kChunk)
     atomicAdd(bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV + cbase + threadIdx.x, sm.vsum[threadIdx.x]);
