@@ -556,6 +556,38 @@ def test_mask_epilogue_full_size_properties():
     assert (np.abs((logit - lt).cpu().numpy()) <= tol).all() and (est - et).abs().max().item() <= 1e-5
 
 
+def test_step_variants_agree_simt_kernel_and_no_pdl():
+    """rmnet_frame_step through the fp32 FFMA kernel (ordinary launches inside the chain) and with programmatic dependent
+    launch switched off (RMNET_DISABLE_PDL=1) gives the same boxes and, within the strict tolerance, the same mem_val as
+    the default tcgen05 + PDL chain."""
+    n, T, H, W = 3, 3, 240, 432
+    s = _regional_setup(85, n, T, H, W)
+    variants = {"umma_pdl": dict(impl=rmnet_b200.RMNET_IMPL_AUTO, env=None), "simt": dict(impl=rmnet_b200.RMNET_IMPL_SIMT, env=None),
+                "umma_no_pdl": dict(impl=rmnet_b200.RMNET_IMPL_AUTO, env="1")}
+    outs = {}
+    for name, v in variants.items():
+        rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=DEV, impl=v["impl"])
+        old = os.environ.pop("RMNET_DISABLE_PDL", None)
+        if v["env"]:
+            os.environ["RMNET_DISABLE_PDL"] = v["env"]
+        try:
+            res = []
+            for t in range(T):
+                m, pb, cb = rm.step(cu(s["mk"][:, :, t]), cu(s["mv"][:, :, t]), cu(s["masks"][t][None]), cu(s["flow"][None]),
+                                    cu(s["qk"]), cu(s["qv"]), commit=(t < T - 1))
+                res.append((m.clone(), pb.clone(), cb.clone()))
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("RMNET_DISABLE_PDL", None)
+            if old is not None:
+                os.environ["RMNET_DISABLE_PDL"] = old
+        outs[name] = res
+    for name in ("simt", "umma_no_pdl"):
+        for (m, pb, cb), (m0, pb0, cb0) in zip(outs[name], outs["umma_pdl"]):
+            assert torch.equal(pb, pb0) and torch.equal(cb, cb0)
+            assert (m - m0).abs().max().item() <= (TOL_STRICT if name == "simt" else 1e-6)
+
+
 def test_step_matches_the_reference_composition_at_full_size():
     """RegionalMemory.step against the reference's own composition of the frame step on this GPU (tests/ref_composition.py:
     torch's CUDA ops for pad / warp / interpolate / bmm / softmax / cat and the UNMODIFIED reference CUDA kernel for both
