@@ -8,4 +8,5 @@ from ._lib import (CH_ABSENT, CH_KEEP, CH_NEW, ELEM_BF16, ELEM_FP16, RMNET_IMPL_
                    RMNET_PREC_SPLIT3, build, lib)
 from .modules import (MemoryReader, RegionalAttentionMapGenerator, RegionalAttentionMapGeneratorFunction,  # noqa: F401
                       RegionalMemory, get_att_map, install, warp)
+from .frame_loop import RegionalFrameLoop  # noqa: F401
 from .ops import MemoryBank, mask_epilogue, update_optical_flow  # noqa: F401

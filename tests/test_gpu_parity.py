@@ -617,6 +617,101 @@ def test_step_matches_the_reference_composition_at_full_size():
             ref.commit(cur)
 
 
+def _toy_nets(seed, dev):
+    """Deterministic stand-ins for the reference's three conv nets (out of scope): 16x average pooling + fixed 1x1
+    projections, and a bilinear x16 up-sampling decoder.  Only their shapes and determinism matter here."""
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    Wk = (torch.randn(128, 5, generator=g) * 0.6).to(dev)
+    Wv = torch.randn(512, 5, generator=g).to(dev)
+    Wkq = (torch.randn(128, 3, generator=g) * 0.6).to(dev)
+    Wvq = torch.randn(512, 3, generator=g).to(dev)
+    Wd = (torch.randn(2, 1024, generator=g) * 0.15).to(dev)
+
+    def memorize_net(frame_p, m, o):
+        x = torch.cat([frame_p.expand(m.shape[0], -1, -1, -1), m[:, None], o[:, None]], dim=1)
+        x = F.avg_pool2d(x, 16)
+        return torch.einsum("oc,nchw->nohw", Wk, x).contiguous(), torch.einsum("oc,nchw->nohw", Wv, x).contiguous()
+
+    def query_net(frame_p):
+        x = F.avg_pool2d(frame_p, 16)
+        return torch.einsum("oc,nchw->nohw", Wkq, x).contiguous(), torch.einsum("oc,nchw->nohw", Wvq, x).contiguous(), None
+
+    def decoder_net(m4, ctx):
+        y = torch.einsum("oc,nchw->nohw", Wd, m4)
+        return F.interpolate(y, scale_factor=16, mode="bilinear", align_corners=False).contiguous()
+
+    return memorize_net, query_net, decoder_net
+
+
+def test_frame_loop_matches_the_reference_loop_restated():
+    """rmnet_b200.RegionalFrameLoop (GPU-resident mirror of RMNet.forward, models/rmnet.py:385-452) against the same loop
+    restated with the reference's composition (tests/ref_composition.py: torch CUDA ops + the unmodified reference
+    kernel) and torch's ops for the tail (:368-380, :289-302, :436-450), with the same stand-in conv nets on both sides:
+    a 9-frame 240x432 clip, 2 -> 3 objects (a new object appears at frame 4), memorize_every = 3."""
+    gen = _ref_generator()
+    if gen is None:
+        pytest.skip("oracle/_ref/reg_att_map_generator*.so not built (make -C oracle ref)")
+    import torch.nn.functional as F
+    from ref_composition import ReferenceClip, pad16
+    from rmnet_b200.frame_loop import RegionalFrameLoop, object_batches
+    H, W, K, n_frames, every = 240, 432, 11, 9, 3
+    rng = np.random.default_rng(91)
+    frames = cu(rng.standard_normal((1, n_frames, 3, H, W)).astype(np.float32))
+    flows = cu((rng.standard_normal((1, n_frames, 2, H, W)) * 1.5).astype(np.float32))
+    labs = []
+    for t in range(n_frames):
+        lab = np.zeros((H, W), np.int64)
+        lab[40 + 2 * t:120 + 2 * t, 60 + 3 * t:200 + 3 * t] = 1
+        lab[130:210, 250 - 2 * t:380 - 2 * t] = 2
+        if t >= 4:
+            lab[20:90, 300:400] = 3                     # object 3 is first annotated at frame 4
+        labs.append(synth.onehot(lab, K))
+    masks = cu(np.stack(labs)[None].astype(np.int32))
+    n_objects = torch.tensor([[2] * 4 + [3] * (n_frames - 4)])
+    nets = _toy_nets(5, DEV)
+
+    loop = RegionalFrameLoop(*nets)
+    est = loop(frames, masks, flows, n_objects, every)
+
+    # ---- the reference loop, restated (models/rmnet.py:385-452)
+    memorize_net, query_net, decoder_net = nets
+    n = int(n_objects.max())
+    ref = ReferenceClip(gen, n, K, H, W)
+    est_ref = torch.zeros_like(est)
+    est_ref[:, 0] = masks[:, 0]
+    existing = torch.unique(torch.argmax(masks[0, 0], dim=0)).cpu().tolist()
+    to_memorize = list(range(0, n_frames, every))
+    new_at = [j for j in range(1, n_frames) if (n_objects[:, j] != n_objects[:, j - 1]).any()]
+    boxes_ref = []
+    for t in range(1, n_frames):
+        prev_mask = est_ref[:, t - 1]
+        m, o = object_batches(pad16(prev_mask, H, W), n)
+        k4, v4 = memorize_net(pad16(frames[:, t - 1], H, W), m, o)
+        k4q, v4q, ctx = query_net(pad16(frames[:, t], H, W))
+        cur = dict(mask=prev_mask[0], flow=flows[0, t], k4=k4, v4=v4, qk=k4q[0], qv=v4q[0])
+        m4, pb, cb = ref.step(cur)
+        boxes_ref.append((pb, cb))
+        if t - 1 in to_memorize or t - 1 in new_at:
+            ref.commit(cur)
+        logits = decoder_net(m4, ctx)
+        modes = [oracle.CH_KEEP] * K
+        if t in new_at:
+            for j in torch.unique(torch.argmax(masks[0, t], dim=0)).cpu().tolist():
+                if j not in existing:
+                    existing.append(j)
+                    modes[j] = oracle.CH_NEW
+        for j in range(n + 1):
+            if j not in existing:
+                modes[j] = oracle.CH_ABSENT
+        _, e = _torch_mask_epilogue(logits, K, H, W, modes, masks[0, t])
+        est_ref[:, t] = e
+    for (pb, cb), (pb_r, cb_r) in zip(loop.last_bboxes, boxes_ref):
+        assert torch.equal(pb, pb_r) and torch.equal(cb, cb_r)
+    assert (est - est_ref).abs().max().item() <= 1e-4
+    assert (est[0, 4, 3] > 0.5).any() and (est[0, 3, 3] < 1e-6).all()    # the new object exists from frame 4 on, not before
+
+
 def test_captured_step_replays_like_eager_steps():
     """RegionalMemory.capture_step: the PDL-chained step as a CUDA graph over static inputs == eager step() on the same
     sequence of frames (non-commit graph and commit graph, as the reference loop alternates them, models/rmnet.py:424)."""
