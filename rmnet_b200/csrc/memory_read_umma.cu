@@ -198,7 +198,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
                         const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
                         const int *__restrict__ q_rects, int h, int w,
                         float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
-                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg) {
+                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg, int dbg_flags) {
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -268,6 +268,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
           if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->k_empty[s]), ((kt / KST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->k_full[s]);
+          if ((dbg_flags & 1) && kt >= KST) { mbar_arrive(full); continue; }  // dev experiment: no TMA traffic after the ring fill (results are garbage)
           mbar_expect_tx(full, use_lo ? K_STAGE_BYTES : K_PLANE_BYTES);
           const uint32_t dst = k_smem + s * K_STAGE_BYTES;
           const int m0 = (pc.tile_begin + it) * MT;
@@ -291,6 +292,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
           if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->v_empty[s]), ((vt / VST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->v_full[s]);
+          if ((dbg_flags & 1) && vt >= VST) { mbar_arrive(full); continue; }
           mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
           const uint32_t dst = v_smem + s * V_STAGE_BYTES;
           const int m0 = (pc.tile_begin + it) * MT;
@@ -470,6 +472,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         TMEM_LD16(s_addr + 48, sr, 48);
         tc_wait_ld();
         if (tstamp && first_piece && it == 0 && row == 0) tstamp[3] = clock64();
+        long long t_s1 = 0;
+        if (tstamp && first_piece && it == 1 && row == 0) t_s1 = clock64();  // dev: S of the second tile is in registers
         if (dbg && first_piece && it == 0 && blockIdx.x == 0) {
 #pragma unroll
           for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
@@ -532,6 +536,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[b]));
+        if (tstamp && first_piece && it == 1 && row == 0) tstamp[15] = clock64();
+        if (tstamp && first_piece && it == 1 && row == 0) tstamp[14] = t_s1;
       }
       gt_done = gt;
       // (max, sum) statistics of the piece for merge.cu
@@ -585,6 +591,7 @@ int make_map(CUtensorMap *m, void *base, uint64_t d0, uint64_t d1, uint64_t d2, 
 }
 
 thread_local float *g_dbg = nullptr;
+thread_local int g_dbg_flags = 0;
 
 }  // namespace
 
@@ -643,7 +650,7 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
     }                                                                                                                    \
     RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
                              bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
-                             temp_rects, bank.cap, g_dbg));                                                              \
+                             temp_rects, bank.cap, g_dbg, g_dbg_flags));                                                 \
   } while (0)
   if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
   else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);
@@ -658,3 +665,5 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
 
 // development hook (not part of the public header): dump S of the first tile of CTA (0,0,0) into `ptr` (128*64 + 128 floats)
 extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_dump(float *ptr) { rmnet::g_dbg = ptr; }
+// development hook: bit 0 = the TMA producers stop loading after the first ring fill (timing experiment only: results are garbage)
+extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_flags(int flags) { rmnet::g_dbg_flags = flags; }

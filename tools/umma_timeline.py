@@ -5,6 +5,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench, rmnet_b200
 L = rmnet_b200.lib()
 L.rmnet_debug_set_umma_dump.argtypes = [ctypes.c_void_p]; L.rmnet_debug_set_umma_dump.restype = None
+L.rmnet_debug_set_umma_flags.argtypes = [ctypes.c_int]; L.rmnet_debug_set_umma_flags.restype = None
+NO_TMA = "no_tma" in sys.argv   # experiment: producers stop loading after the ring fill -> is the tile time bound by the tile traffic?
 dev = torch.device("cuda:0")
 for wlname in ("c2", "c3"):
     wl = bench.WORKLOADS[wlname]; n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
@@ -24,11 +26,13 @@ for wlname in ("c2", "c3"):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev); flush.zero_()
         torch.cuda.synchronize()
     L.rmnet_debug_set_umma_dump(dbg.data_ptr())
+    if NO_TMA: L.rmnet_debug_set_umma_flags(1)
     if standalone:
         rm.bank.read(d["qk"], d["qv"], rq0, n, stages=1)
     else:
         rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
     torch.cuda.synchronize()
+    L.rmnet_debug_set_umma_flags(0)
     L.rmnet_debug_set_umma_dump(None)
     ts = dbg[8448:8448 + 148 * 32].view(torch.int64).view(148, 16).cpu().numpy()
     live = ts[:, 6] > 0
@@ -50,5 +54,8 @@ for wlname in ("c2", "c3"):
     rqn = rq[0, 1:n + 1].cpu().numpy()
     st = rm.bank.stats()
     print("   cells/object", (st[:n, 0] + st[:n, 1]).tolist(), "query cells/object", [int(max(0, r[1]-r[0]+1) * max(0, r[3]-r[2]+1)) for r in rqn])
+    wg = (t[:, 15] - t[:, 14]).astype(np.float64)
+    wg = wg[(t[:, 15] > 0) & (t[:, 14] > 0)]
+    if len(wg): print(f"   softmax warpgroup, second tile: S in registers -> P stored and signalled: median {np.median(wg):.0f} cycles (max {wg.max():.0f})")
     per_tile = (rel[:, 3] - rel[:, 2]) / np.maximum(t[:, 7] - 1, 1)
     print(f"   steady state cycles per tile (median) {np.median(per_tile):.0f}")
