@@ -1,16 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- the regional memory-read hot path of RMNet on B200, measured per frame.
 
-A "step" is ONE frame of one clip through the hot path, in the steady state of a clip:
+A "step" is ONE frame of one clip through the hot path, in the steady state of a clip -- one
+call of RegionalMemory.step = rmnet_frame_step = four kernels chained by programmatic dependent launch:
 
-    memorise side :  generator(prev_mask padded [1,11,Hp,Wp]) -> cell rects -> pack k4/v4 of the previous frame
-                     into the memory bank as its temporary last frame          (models/rmnet.py:239-248, :416-426)
-    segment side  :  fused warp + threshold + bbox(prev_mask [1,11,H,W], flow) -> cell rects
-                     -> regional memory read for all objects -> mem_val [n,1024,h,w]   (:431, :307, :355-361, :147-165)
+    regions : one pass over prev_mask [1,11,H,W] + flow -> the box of the zero-padded mask (memorise side,
+              models/rmnet.py:212 + :244) AND the box of the flow-warped mask (segment side, :431), with their /16 cell
+              rectangles (:245, :307 + :356)
+    pack    : k4/v4 of the previous frame into the memory bank as its temporary last frame (:239-248, :416-426) +
+              the query side: k4q * att16 packed for the tensor cores, v4q * att16 into mem_val[:, 512:] (:355-358, :163)
+    read    : tcgen05 split-KV attention of all objects against the region-compacted bank (:147-165)
+    merge   : split combination + masked-cell correction + uniform rows -> mem_val [n,1024,h,w]
 
 The ResNet-50 encoders / decoder that produce k4/v4 and consume mem_val are the reference's cuDNN code and out of
 scope: their outputs are synthetic tensors of the right shape.  Metric: frames/sec of this path
 (BASELINE.json `metric`), `value` with inputs resident in HBM, `e2e` through the public API with pinned HOST buffers.
+Extra legs on rank 0 at N = 1: the step replayed as a CUDA graph, the reference's own composition of the step on the
+same GPU (torch CUDA ops + its unmodified CUDA kernel), the attention kernel alone (roofline), the CPU port.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
 """
