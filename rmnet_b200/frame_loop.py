@@ -40,6 +40,32 @@ def object_batches(masks_p, n):
     return torch.cat(m, dim=0), torch.cat(o, dim=0)
 
 
+def memorize_schedule(n_frames, memorize_every, n_objects_per_frame):
+    """Host logic of models/rmnet.py:405-408, :424: -> (to_memorize, contains_new_objects, commit[t] for t = 1..F-1, #commits).
+    Frame t-1 is committed to the permanent memory iff it is a multiple of memorize_every or a frame whose object count
+    differs from its predecessor's."""
+    to_memorize = set(range(0, n_frames, memorize_every))
+    new_at = {j for j in range(1, n_frames) if n_objects_per_frame[j] != n_objects_per_frame[j - 1]}
+    commit = {t: ((t - 1) in to_memorize or (t - 1) in new_at) for t in range(1, n_frames)}
+    return to_memorize, new_at, commit, sum(commit.values())
+
+
+def channel_modes(K, n_max, existing, labels_in_gt):
+    """Host logic of models/rmnet.py:436-448 for one frame: `existing` (list, updated in place) are the objects seen so
+    far; `labels_in_gt` = the labels present in masks[i, t] when t introduces objects, else None.
+    -> per-channel modes for rmnet_mask_epilogue_forward (CH_KEEP / CH_NEW / CH_ABSENT)."""
+    modes = [CH_KEEP] * K
+    if labels_in_gt is not None:
+        for j in labels_in_gt:
+            if j not in existing:
+                existing.append(j)
+                modes[j] = CH_NEW                      # logit := masks[i,t,j] * 32.0605 - 16.1181  (:442)
+    for j in range(n_max + 1):
+        if j not in existing:
+            modes[j] = CH_ABSENT                       # logit := -16.1181                          (:448)
+    return modes
+
+
 class RegionalFrameLoop:
     """forward(frames, masks, optical_flows, n_objects, memorize_every) -> est_masks [1,F,K,H,W], the signature and the
     semantics of RMNet.forward (models/rmnet.py:385) for batch 1; est_masks stays on the device."""
@@ -65,9 +91,7 @@ class RegionalFrameLoop:
         est_masks = torch.zeros((1, n_frames, K, H, W), dtype=torch.float32, device=dev)   # :387 (kept on the device)
         est_masks[:, 0] = masks[:, 0]                                               # :396
         existing = torch.unique(torch.argmax(masks[0, 0], dim=0)).cpu().tolist()    # :399-402
-        to_memorize = set(range(0, n_frames, memorize_every))                       # :405
-        new_at = {j for j in range(1, n_frames) if bool((n_obj_host[:, j] != n_obj_host[:, j - 1]).any())}   # :406-408
-        n_commits = sum(1 for t in range(1, n_frames) if (t - 1) in to_memorize or (t - 1) in new_at)
+        _, new_at, commit_at, n_commits = memorize_schedule(n_frames, memorize_every, n_obj_host[0].tolist())   # :405-408
         rm = RegionalMemory(n, (H, W), max_frames=n_commits + 1, device=dev, precision=self.precision, impl=self.impl,
                             elem_format=self.elem_format)
         self.last_bboxes = []
@@ -78,23 +102,15 @@ class RegionalFrameLoop:
             m, o = object_batches(masks_p, n)                                       # :219-229
             k4, v4 = self.memorize_net(frame_p, m, o)                               # :234-236
             k4q, v4q, ctx = self.query_net(F.pad(frames[:, t], pad))                # :307-315
-            commit = (t - 1) in to_memorize or (t - 1) in new_at                    # :424
+            commit = commit_at[t]                                                   # :424
             m4, prev_bbox, curr_bbox = rm.step(k4.contiguous(), v4.contiguous(), prev_mask.contiguous(),
                                                optical_flows[:, t].contiguous(), k4q[0].contiguous(), v4q[0].contiguous(),
                                                commit=commit)                       # :239-248, :416-426, :431, :355-361
             self.last_bboxes.append((prev_bbox.clone(), curr_bbox.clone()))
             logits = self.decoder_net(m4, ctx)                                      # :366
-            modes = [CH_KEEP] * K
-            new_mask = None
-            if t in new_at:                                                         # :436-442
-                for j in torch.unique(torch.argmax(masks[0, t], dim=0)).cpu().tolist():
-                    if j not in existing:
-                        existing.append(j)
-                        modes[j] = CH_NEW
-                new_mask = masks[0, t].to(torch.int32).contiguous()
-            for j in range(n + 1):                                                  # :445-448
-                if j not in existing:
-                    modes[j] = CH_ABSENT
+            labels = torch.unique(torch.argmax(masks[0, t], dim=0)).cpu().tolist() if t in new_at else None   # :436-438
+            modes = channel_modes(K, n, existing, labels)                           # :439-448
+            new_mask = masks[0, t].to(torch.int32).contiguous() if t in new_at else None
             _, est = ops.mask_epilogue(logits.contiguous(), K, (H, W), modes, new_mask, want_logit=False)   # :368-380, :289-302, :450
             est_masks[:, t] = est
         return est_masks

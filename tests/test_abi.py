@@ -91,3 +91,29 @@ def test_cell_rect_closed_form_equals_pad_then_downsample():
         if cx0 <= cx1 and cy0 <= cy1:
             ref[cy0:cy1 + 1, cx0:cx1 + 1] = 1
         np.testing.assert_array_equal(a16, ref)
+
+
+def test_frame_loop_host_logic_matches_the_reference_rules():
+    """rmnet_b200.frame_loop: the memorise schedule (models/rmnet.py:405-408, :424) and the per-frame channel overrides
+    (:436-448), against a literal restatement of the reference's loops."""
+    from rmnet_b200.frame_loop import CH_ABSENT, CH_KEEP, CH_NEW, channel_modes, memorize_schedule
+    for n_frames, every, nobj in ((16, 5, [1] * 16), (12, 3, [2] * 4 + [3] * 5 + [4] * 3), (7, 1, [1, 1, 2, 2, 2, 3, 3]), (3, 10, [2, 2, 2])):
+        to_mem, new_at, commit, n_commits = memorize_schedule(n_frames, every, nobj)
+        ref_to_mem = [j for j in range(0, n_frames, every)]
+        ref_new = [j for j in range(1, n_frames) if nobj[j] != nobj[j - 1]]
+        assert sorted(to_mem) == ref_to_mem and sorted(new_at) == ref_new
+        T = 0   # the reference's bank length: `keys` grows by one frame whenever t-1 is committed (:424-426)
+        for t in range(1, n_frames):
+            ref_commit = (t - 1 in ref_to_mem) or (t - 1 in ref_new)
+            assert commit[t] == ref_commit
+            T += int(ref_commit)
+        assert T == n_commits
+    # SURVEY 3.1: with memorize_every = 5, T(t) = 1 + #{j in {0,5,10,...} : j < t-1} ... the bank reaches 20 committed frames at t = 96
+    _, _, commit, _ = memorize_schedule(100, 5, [1] * 100)
+    assert sum(commit[t] for t in range(1, 97)) == 20
+    K, n_max = 11, 3
+    existing = [0, 1]
+    assert channel_modes(K, n_max, existing, None) == [CH_KEEP, CH_KEEP, CH_ABSENT, CH_ABSENT] + [CH_KEEP] * 7
+    m = channel_modes(K, n_max, existing, [0, 1, 3])          # object 3 is first annotated in this frame
+    assert m == [CH_KEEP, CH_KEEP, CH_ABSENT, CH_NEW] + [CH_KEEP] * 7 and existing == [0, 1, 3]
+    assert channel_modes(K, n_max, existing, [0, 1, 3]) == [CH_KEEP, CH_KEEP, CH_ABSENT, CH_KEEP] + [CH_KEEP] * 7
