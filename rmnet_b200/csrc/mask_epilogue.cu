@@ -28,7 +28,9 @@ struct ChannelModes {
 // NOBJ = compile-time bound on n_obj: the channels 0..n_obj (background + real objects) are the only ones with per-pixel
 // transcendental work and live in registers (unrolled); the channels above n_obj are the clamp floor or a whole-channel
 // override -- constants per pixel -- and are walked by a plain runtime loop.  Summation orders are the reference's.
-template <int NOBJ>
+// HI_MODES = false: no override among the channels above n_obj (always the case in the reference's loop, whose overrides
+// touch j <= n_max_objects only): those channels are the clamp floor and need no mode decoding at all.
+template <int NOBJ, bool HI_MODES>
 __global__ void __launch_bounds__(kThreads)
 mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int H, int W, int Hp, int Wp, int pad_l, int pad_t,
                      ChannelModes modes, const int *__restrict__ new_mask, float *__restrict__ logit_out,
@@ -36,7 +38,8 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
   const long long n_pixels = (long long)H * W;
   const long long j = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (j >= n_pixels) return;
-  const int y = (int)(j / W), x = (int)(j - (long long)y * W);
+  const unsigned uj = (unsigned)j;  // H * W < 2^31 (checked by the host): 32-bit division
+  const int y = (int)(uj / (unsigned)W), x = (int)(uj - (unsigned)y * (unsigned)W);
   const long long jp = (long long)(y + pad_t) * Wp + (x + pad_l);  // the same pixel in the padded decoder output
   const long long plane_p = (long long)Hp * Wp;
   const float lo = (float)1e-7, hi = (float)(1.0 - 1e-7);  // torch.clamp casts its python-float bounds to float32
@@ -84,7 +87,7 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
     }
   }
   for (int c = n_obj + 1; c < K; ++c) {
-    const float v = const_channel(c, modes.get(c));
+    const float v = HI_MODES ? const_channel(c, modes.get(c)) : floor_logit;
     if (logit_out) logit_out[(long long)c * n_pixels + j] = v;
     mx = fmaxf(mx, v);
   }
@@ -99,7 +102,7 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
     }
   }
   for (int c = n_obj + 1; c < K; ++c) {
-    const int mode = modes.get(c);
+    const int mode = HI_MODES ? modes.get(c) : RMNET_CH_KEEP;
     sum = __fadd_rn(sum, mode == RMNET_CH_KEEP ? e_floor : expf(__fsub_rn(const_channel(c, mode), mx)));
   }
   // ---- pass 3: exp(x - max) / sum; the floor channels share one quotient
@@ -108,7 +111,7 @@ mask_epilogue_kernel(const float *__restrict__ dec_logits, int n_obj, int K, int
     if (c <= n_obj) est_mask[(long long)c * n_pixels + j] = __fdiv_rn(lg[c], sum);
   const float q_floor = __fdiv_rn(e_floor, sum);
   for (int c = n_obj + 1; c < K; ++c) {
-    const int mode = modes.get(c);
+    const int mode = HI_MODES ? modes.get(c) : RMNET_CH_KEEP;
     est_mask[(long long)c * n_pixels + j] =
         mode == RMNET_CH_KEEP ? q_floor : __fdiv_rn(expf(__fsub_rn(const_channel(c, mode), mx)), sum);
   }
@@ -126,6 +129,7 @@ int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, int K, int H
   RMNET_CHECK_ARG(dec_logits && est_mask, "null pointer argument");
   RMNET_CHECK_ARG(n_obj > 0 && K >= 2 && n_obj < K && K <= 64, "bad shape n_obj=%d K=%d (need 0 < n_obj < K <= 64)", n_obj, K);
   RMNET_CHECK_ARG(H > 0 && W > 0 && pad_l >= 0 && pad_r >= 0 && pad_t >= 0 && pad_b >= 0, "bad frame size / padding");
+  RMNET_CHECK_ARG((long long)H * W < (1LL << 31), "frame too large");
   ChannelModes modes;
   memset(&modes, 0, sizeof(modes));
   bool any_new = false;
@@ -142,9 +146,17 @@ int rmnet_mask_epilogue_forward(const float *dec_logits, int n_obj, int K, int H
   const long long n_pixels = (long long)H * W;
   dim3 grid((unsigned)((n_pixels + kThreads - 1) / kThreads));
   cudaStream_t st = (cudaStream_t)stream;
+  bool hi_modes = false;
+  for (int c = n_obj + 1; c < K; ++c) hi_modes |= modes.get(c) != RMNET_CH_KEEP;
 #define RMNET_LAUNCH_EPI(NO)                                                                                                   \
-  mask_epilogue_kernel<NO><<<grid, kThreads, 0, st>>>(dec_logits, n_obj, K, H, W, Hp, Wp, pad_l, pad_t, modes, new_mask, logit_out, \
-                                                      est_mask)
+  do {                                                                                                                         \
+    if (hi_modes)                                                                                                              \
+      mask_epilogue_kernel<NO, true><<<grid, kThreads, 0, st>>>(dec_logits, n_obj, K, H, W, Hp, Wp, pad_l, pad_t, modes, new_mask, \
+                                                                logit_out, est_mask);                                         \
+    else                                                                                                                       \
+      mask_epilogue_kernel<NO, false><<<grid, kThreads, 0, st>>>(dec_logits, n_obj, K, H, W, Hp, Wp, pad_l, pad_t, modes, new_mask, \
+                                                                 logit_out, est_mask);                                        \
+  } while (0)
   if (n_obj <= 5) RMNET_LAUNCH_EPI(5);         // DAVIS-like clips
   else if (n_obj <= 11) RMNET_LAUNCH_EPI(11);  // YouTube-VOS-like clips (N_MAX_OBJECTS = 10)
   else if (n_obj <= 31) RMNET_LAUNCH_EPI(31);
