@@ -36,7 +36,12 @@ def _ref_generator():
         return None
     if os.path.dirname(so[0]) not in sys.path:
         sys.path.insert(0, os.path.dirname(so[0]))
-    import reg_att_map_generator  # the reference's own pybind module, compiled from its unmodified sources
+    try:
+        import reg_att_map_generator  # the reference's own pybind module, compiled from its unmodified sources
+    except (ImportError, OSError):    # built against another torch: treat like "not built" (the tests that need it skip)
+        return None
+    if not hasattr(reg_att_map_generator, "forward") or "oracle" not in (getattr(reg_att_map_generator, "__file__", "") or ""):
+        return None                   # e.g. the drop-in module of the same name was imported first
     return reg_att_map_generator
 
 
