@@ -312,7 +312,7 @@ __device__ __forceinline__ void warp_box_to_smem(int *s_acc, unsigned ballot, bo
 }
 
 template <int ORDER, bool DIRECT>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)  // 4 CTAs per SM = the one-wave grid of launch_frame_boxes (the warp-only variant took 80 registers uncapped)
 frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict__ flow, int K, int H, int W,
                    float inv_w, float inv_h, float thr, BoxFinalize fin_warp, BoxFinalize fin_direct,
                    int *__restrict__ bboxes_warp, int *__restrict__ bboxes_direct, int *__restrict__ ws,
