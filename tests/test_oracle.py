@@ -151,6 +151,49 @@ def test_generator_semantics_edge_cases():
         np.testing.assert_array_equal(att[0, i], ref)
 
 
+def test_generator_randomised_against_an_independent_numpy_restatement():
+    """oracle.reg_att_map (C) against an independent numpy restatement of reg_att_map_generator.cu:31-92 on 60 random
+    masks: sparse / dense foregrounds, NaNs, objects touching the borders, other thresholds and loosening widths."""
+    rng = np.random.default_rng(123)
+
+    def numpy_generator(mask, thr, n_pts, loose):
+        B, K, H, W = mask.shape
+        att = np.zeros_like(mask)
+        bb = np.zeros((B, K, 4), np.int32)
+        for b in range(B):
+            for i in range(1, K):
+                with np.errstate(invalid="ignore"):
+                    ys, xs = np.nonzero(mask[b, i] >= thr)                     # :42 (NaN compares false)
+                if len(xs) < n_pts:                                            # :57-61
+                    x0, x1, y0, y1 = 0, W - 1, 0, H - 1
+                else:                                                          # :63-74
+                    x0 = 0 if xs.min() <= loose else xs.min() - loose
+                    x1 = W - 1 if xs.max() + loose >= W else xs.max() + loose
+                    y0 = 0 if ys.min() <= loose else ys.min() - loose
+                    y1 = H - 1 if ys.max() + loose >= H else ys.max() + loose
+                bb[b, i] = (x0, x1, y0, y1)
+                att[b, i, y0:y1 + 1, x0:x1 + 1] = 1                            # :81-92
+        return att, bb
+
+    for case in range(60):
+        B, K = int(rng.integers(1, 3)), int(rng.integers(2, 7))
+        H, W = int(rng.integers(8, 150)), int(rng.integers(8, 220))
+        thr = float(rng.choice([0.5, 0.3, 0.9]))
+        n_pts = int(rng.choice([10, 1, 25]))
+        loose = int(rng.choice([64, 0, 7, 300]))
+        m = rng.random((B, K, H, W)).astype(np.float32) * float(rng.choice([0.6, 1.0, 1.4]))
+        if case % 3 == 0:                                                      # sparse: a few pixels above the threshold
+            m *= (rng.random((B, K, H, W)) < 0.002)
+        if case % 4 == 1:
+            m[rng.random((B, K, H, W)) < 0.01] = np.nan
+        if case % 5 == 2:                                                      # an object touching two borders
+            m[:, 1, :3, -3:] = 1.0
+        att, bb = oracle.reg_att_map(m, thr, n_pts, loose)
+        att_ref, bb_ref = numpy_generator(m, thr, n_pts, loose)
+        np.testing.assert_array_equal(bb, bb_ref, err_msg=f"case {case}")
+        np.testing.assert_array_equal(att, att_ref, err_msg=f"case {case}")
+
+
 def test_mask_epilogue_matches_reference_golden(golden_dir):
     """oracle.mask_epilogue vs the reference's soft_aggregation + torch ops (models/rmnet.py:368-380, :289-302, :436-450).
     est_mask (what the frame loop stores, :450) is held to 1e-5; the logit map to 1e-3 (north_star) wherever the
