@@ -80,3 +80,30 @@ class ReferenceClip:
         p = torch.softmax(torch.bmm(mi, k4e.reshape(n, 128, N)) / math.sqrt(128), dim=1)   # :155-157
         mem = torch.bmm(m_val.view(n, 512, M), p).view(n, 512, h, w)                 # :158-161
         return torch.cat([mem, v4e], dim=1), prev_bb, cur_bb                         # :163
+
+
+def _pad_amounts(H, W, d=16):
+    """utils/helpers.py:105-124 -> (lw, uw, lh, uh)"""
+    nh, nw = (H + d - 1) // d * d, (W + d - 1) // d * d
+    lh, lw = (nh - H) // 2, (nw - W) // 2
+    return lw, nw - W - lw, lh, nh - H - lh
+
+
+def torch_mask_epilogue(x, K, H, W, modes, new_mask):
+    """models/rmnet.py:368-380, :289-302, :436-450 with torch's own ops on x's device (what the reference runs there).
+    modes: 0 keep, 1 absent (:448), 2 new object (:442)."""
+    n = x.shape[0]
+    ps = F.softmax(x, dim=1)[:, 1]
+    em = torch.zeros(1, K, *ps.shape[1:], device=x.device)
+    em[0, 0] = torch.prod(1 - ps, dim=0)
+    em[0, 1:n + 1] = ps
+    em = torch.clamp(em, 1e-7, 1 - 1e-7)
+    logit = torch.log((em / (1 - em)))
+    lw, uw, lh, uh = _pad_amounts(H, W)
+    logit = logit[:, :, lh:lh + H, lw:lw + W].clone()
+    for j in range(K):
+        if modes[j] == 2:
+            logit[0, j] = new_mask[j].float() * 32.0605 - 16.1181
+        if modes[j] == 1:
+            logit[0, j] = -16.1181
+    return logit, F.softmax(logit, dim=1)

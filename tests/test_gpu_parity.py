@@ -493,23 +493,8 @@ def test_step_equals_memorize_then_read():
 
 
 def _torch_mask_epilogue(x, K, H, W, modes, new_mask):
-    """models/rmnet.py:368-380, :289-302, :436-450 with torch's own CUDA ops (what the reference runs on this GPU)."""
-    import torch.nn.functional as F
-    n = x.shape[0]
-    ps = F.softmax(x, dim=1)[:, 1]
-    em = torch.zeros(1, K, *ps.shape[1:], device=x.device)
-    em[0, 0] = torch.prod(1 - ps, dim=0)
-    em[0, 1:n + 1] = ps
-    em = torch.clamp(em, 1e-7, 1 - 1e-7)
-    logit = torch.log((em / (1 - em)))
-    lw, uw, lh, uh = oracle.pad_amounts(H, W)
-    logit = logit[:, :, lh:lh + H, lw:lw + W].clone()
-    for j in range(K):
-        if modes[j] == oracle.CH_NEW:
-            logit[0, j] = new_mask[j].float() * 32.0605 - 16.1181
-        if modes[j] == oracle.CH_ABSENT:
-            logit[0, j] = -16.1181
-    return logit, F.softmax(logit, dim=1)
+    from ref_composition import torch_mask_epilogue
+    return torch_mask_epilogue(x, K, H, W, modes, new_mask)
 
 
 def test_mask_epilogue_vs_golden_oracle_and_torch_cuda(golden_dir):

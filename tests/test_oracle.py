@@ -79,6 +79,26 @@ def test_warp_matches_reference_golden_bit_exact(golden_dir):
         assert np.abs(img1c[0] - g[f"c{i}_img1"]).max() < 1e-3
 
 
+def test_warp_randomised_bit_exact_against_torch_cpu_ops():
+    """oracle.warp(arith='cpu') against RMNet.warp restated with torch's own CPU ops (tests/ref_composition.torch_warp,
+    models/rmnet.py:252-278), live, on 24 random cases: odd sizes, B > 1, half-pixel flows, large flows that leave the
+    frame, soft and one-hot images.  Bit-exact, like the golden cases."""
+    import torch
+    from ref_composition import torch_warp
+    torch.set_num_threads(1)
+    rng = np.random.default_rng(77)
+    for case in range(24):
+        B, C = int(rng.integers(1, 3)), int(rng.integers(1, 5))
+        H, W = int(rng.integers(2, 70)), int(rng.integers(2, 90))
+        lab = synth.rect_label_map(rng, max(C - 1, 1), H, W)
+        img = np.stack([synth.soft_masks(rng, lab, C) if case % 2 else synth.onehot(lab, C) for _ in range(B)])
+        flow = np.stack([synth.flow_field(rng, H, W, float(rng.choice([0.5, 2.0, 15.0])), half_pixel=(case % 3 == 0)) for _ in range(B)])
+        ref_img, ref_mask = torch_warp(torch.from_numpy(img), torch.from_numpy(flow))
+        img1, valid = oracle.warp(img, flow, arith="cpu")
+        np.testing.assert_array_equal(img1, ref_img.numpy(), err_msg=f"case {case} {B}x{C}x{H}x{W}")
+        np.testing.assert_array_equal(valid, ref_mask.numpy(), err_msg=f"case {case}")
+
+
 def test_pad_and_downsample_match_reference_golden(golden_dir):
     g = _load(golden_dir, "pad_downsample.npz")
     for i, (H, W) in enumerate(g["sizes"]):
@@ -219,3 +239,37 @@ def test_mask_epilogue_matches_reference_golden(golden_dir):
         assert np.float32(logit.max()) == g[f"c{i}_logit"].max()
         if K > n + 1 and modes[n + 1] == oracle.CH_KEEP:
             assert (logit[0, n + 1] == np.float32(np.log(np.float32(1e-7) / (np.float32(1) - np.float32(1e-7))))).all()
+
+
+def test_mask_epilogue_and_memory_read_randomised_against_torch_cpu_ops():
+    """Live (no stored vectors): oracle.mask_epilogue against the torch composition of models/rmnet.py:368-380, :289-302,
+    :436-450 and oracle.memory_read against MemoryReader's ops (:147-165), both on torch's CPU backend, random shapes."""
+    import math
+    import torch
+    from ref_composition import torch_mask_epilogue
+    torch.set_num_threads(2)
+    rng = np.random.default_rng(131)
+    for case in range(8):
+        n, K = int(rng.integers(1, 6)), 11
+        H, W = int(rng.integers(17, 70)), int(rng.integers(17, 90))
+        x = synth.decoder_logits(rng, n, H, W)
+        modes = [0] * K
+        if case % 2:
+            modes[int(rng.integers(1, n + 1))] = oracle.CH_ABSENT
+        if case % 3 == 0:
+            modes[n] = oracle.CH_NEW
+        new_mask = synth.onehot(synth.rect_label_map(rng, K - 1, H, W), K).astype(np.int32)
+        lt, et = torch_mask_epilogue(torch.from_numpy(x), K, H, W, modes, torch.from_numpy(new_mask))
+        lo, eo = oracle.mask_epilogue(x, K, (H, W), modes, new_mask)
+        assert (np.abs(lo - lt.numpy()) <= synth.epilogue_logit_tolerance(x, K, H, W)).all(), f"case {case}"
+        assert np.abs(eo - et.numpy()).max() <= 1e-5
+    for case in range(6):
+        n, T, h, w = int(rng.integers(1, 4)), int(rng.integers(1, 5)), int(rng.integers(1, 9)), int(rng.integers(1, 11))
+        mk, mv, qk, qv = synth.memory_read_inputs(200 + case, n, T, h, w, float(rng.choice([0.3, 1.0, 2.0])))
+        M, N = T * h * w, h * w
+        mi = torch.transpose(torch.from_numpy(mk).view(n, synth.CK, M), 1, 2)
+        p = torch.softmax(torch.bmm(mi, torch.from_numpy(qk).view(n, synth.CK, N)) / math.sqrt(synth.CK), dim=1)
+        mem = torch.bmm(torch.from_numpy(mv).view(n, synth.CV, M), p).view(n, synth.CV, h, w)
+        ref = torch.cat([mem, torch.from_numpy(qv)], dim=1).numpy()
+        got, p_o = oracle.memory_read(mk, mv, qk, qv, want_p=True)
+        assert np.abs(got - ref).max() <= 2e-5 and np.abs(p_o - p.numpy()).max() <= 2e-6, f"case {case}"
