@@ -7,6 +7,6 @@ reference's compiled extensions).  There is no CPU / PyTorch fallback: a missing
 from ._lib import (CH_ABSENT, CH_KEEP, CH_NEW, ELEM_BF16, ELEM_FP16, RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET_IMPL_UMMA, RMNET_PREC_SINGLE,  # noqa: F401
                    RMNET_PREC_SPLIT3, build, lib)
 from .modules import (MemoryReader, RegionalAttentionMapGenerator, RegionalAttentionMapGeneratorFunction,  # noqa: F401
-                      RegionalMemory, get_att_map, install, warp)
+                      RegionalMemory, fused_forward, get_att_map, install, uninstall, warp)
 from .frame_loop import RegionalFrameLoop  # noqa: F401
 from .ops import MemoryBank, mask_epilogue, update_optical_flow  # noqa: F401

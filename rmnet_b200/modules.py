@@ -195,12 +195,66 @@ class CapturedStep:
         return self.out, self.prev_bbox, self.curr_bbox
 
 
-def install(models_rmnet_module):
-    """Rebind the reference's names so that an unmodified core/inference.py builds an RMNet that runs on this
-    library (RMNet.__init__ looks the classes up at construction time, models/rmnet.py:187-189)."""
+_ORIG = "_rmnet_b200_originals"
+
+
+def fused_forward(self, frames, masks, optical_flows, n_objects, memorize_every, device=None):
+    """RMNet.forward (models/rmnet.py:385) bound by install(): the GPU-resident RegionalFrameLoop built once per model
+    instance from the instance's OWN encoder_memory / kv_memory / encoder_query / kv_query / decoder.  Inference, batch 1
+    (core/inference.py:26, core/test.py) only; a batched or differentiable call is handed to the reference's own forward
+    untouched (training is outside this library's path)."""
+    differentiable = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+    if frames.size(0) != 1 or differentiable:
+        return getattr(type(self), _ORIG)["forward"](self, frames, masks, optical_flows, n_objects, memorize_every, device)
+    from .frame_loop import RegionalFrameLoop
+    opts = getattr(type(self), "_rmnet_b200_options")
+    loop = self.__dict__.get("_rmnet_b200_loop")
+    if loop is None or loop._options is not opts:
+        loop = RegionalFrameLoop.from_rmnet(self, **opts)
+        loop._options = opts
+        object.__setattr__(self, "_rmnet_b200_loop", loop)
+    return loop.forward(frames, masks, optical_flows, n_objects, memorize_every, device)
+
+
+def install(models_rmnet_module, fused=True, use_graph=None, output="reference", precision=RMNET_PREC_SPLIT3,
+            impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16):
+    """Rebind the reference's names so that an unmodified core/inference.py builds an RMNet that runs on this library
+    (RMNet.__init__ looks the classes up at construction time, models/rmnet.py:187-189; core/inference.py:17 imports the
+    RMNet class itself, so its methods are patched in place):
+
+      MemoryReader, RegionalAttentionMapGenerator, RMNet.warp, RMNet.get_att_map  -> the literal operator drop-ins;
+      RMNet.forward (fused=True)  -> fused_forward: the whole frame loop on the fused regional path.  RMNet.memorize /
+      RMNet.segment keep the reference's bodies (they are only reached through the reference's own forward, i.e. batched /
+      training calls, where every op of theirs that is on the path already resolves to the literal drop-ins above).
+
+    use_graph: replay each frame as one CUDA graph (None = on unless RMNET_B200_GRAPH=0); output: see RegionalFrameLoop.
+    uninstall() restores the reference's own attributes."""
+    import os
+    cls = models_rmnet_module.RMNet
+    if not hasattr(cls, _ORIG):
+        setattr(cls, _ORIG, {"forward": cls.forward, "warp": cls.warp, "get_att_map": cls.get_att_map,
+                             "MemoryReader": models_rmnet_module.MemoryReader,
+                             "RegionalAttentionMapGenerator": models_rmnet_module.RegionalAttentionMapGenerator})
     models_rmnet_module.MemoryReader = MemoryReader
     models_rmnet_module.RegionalAttentionMapGenerator = RegionalAttentionMapGenerator
-    cls = models_rmnet_module.RMNet
     cls.warp = lambda self, img0, flow: warp(img0, flow)
     cls.get_att_map = lambda self, prev_mask, flow=None: get_att_map(prev_mask, flow)
+    if use_graph is None:
+        use_graph = os.environ.get("RMNET_B200_GRAPH", "1") != "0"
+    cls._rmnet_b200_options = dict(use_graph=bool(use_graph), output=output, precision=precision, impl=impl, elem_format=elem_format)
+    if fused:
+        cls.forward = fused_forward
+    return models_rmnet_module
+
+
+def uninstall(models_rmnet_module):
+    """Undo install(): the reference's own forward / warp / get_att_map / MemoryReader / generator are back."""
+    cls = models_rmnet_module.RMNet
+    orig = getattr(cls, _ORIG, None)
+    if orig is None:
+        return models_rmnet_module
+    cls.forward, cls.warp, cls.get_att_map = orig["forward"], orig["warp"], orig["get_att_map"]
+    models_rmnet_module.MemoryReader = orig["MemoryReader"]
+    models_rmnet_module.RegionalAttentionMapGenerator = orig["RegionalAttentionMapGenerator"]
+    delattr(cls, _ORIG)
     return models_rmnet_module

@@ -662,7 +662,7 @@ def test_frame_loop_matches_the_reference_loop_restated():
     nets = _toy_nets(5, DEV)
 
     loop = RegionalFrameLoop(*nets)
-    est = loop(frames, masks, flows, n_objects, every)
+    est = loop(frames, masks, flows, n_objects, every, keep_bboxes=True)
 
     # ---- the reference loop, restated (models/rmnet.py:385-452)
     memorize_net, query_net, decoder_net = nets
