@@ -1,8 +1,9 @@
 #!/usr/bin/env python
-"""bench.py -- the regional memory-read hot path of RMNet on B200, measured per frame.
+"""bench.py -- RMNet's per-frame regional memory-read hot path on B200, and the VOS frames/sec it yields.
 
-A "step" is ONE frame of one clip through the hot path, in the steady state of a clip -- one
-call of RegionalMemory.step = rmnet_frame_step = four kernels chained by programmatic dependent launch:
+`value` (device-timed, inputs resident in HBM): a "step" is ONE frame of one clip through the hot path (SURVEY 8a rows
+a2-a10) in the steady state of a clip -- one call of RegionalMemory.step = rmnet_frame_step = four kernels chained by
+programmatic dependent launch:
 
     regions : one pass over prev_mask [1,11,H,W] + flow -> the box of the zero-padded mask (memorise side,
               models/rmnet.py:212 + :244) AND the box of the flow-warped mask (segment side, :431), with their /16 cell
@@ -12,13 +13,24 @@ call of RegionalMemory.step = rmnet_frame_step = four kernels chained by program
     read    : tcgen05 split-KV attention of all objects against the region-compacted bank (:147-165)
     merge   : split combination + masked-cell correction + uniform rows -> mem_val [n,1024,h,w]
 
-The ResNet-50 encoders / decoder that produce k4/v4 and consume mem_val are the reference's cuDNN code and out of
-scope: their outputs are synthetic tensors of the right shape.  Metric: frames/sec of this path
-(BASELINE.json `metric`), `value` with inputs resident in HBM, `e2e` through the public API with pinned HOST buffers.
-Extra legs on rank 0 at N = 1: the step replayed as a CUDA graph, the reference's own composition of the step on the
-same GPU (torch CUDA ops + its unmodified CUDA kernel), the attention kernel alone (roofline), the CPU port.
+`e2e` (the headline): 480p VOS frames/sec through the reference-facing API -- the two calls utils/helpers.py:55-56 makes
+per clip, `tflownet(frames)` and `rmnet(frames, masks, flows, n_objects, 5)`, on HOST tensors, with the UNMODIFIED
+reference nets (ResNet-50 encoders, decoder, TinyFlowNet: cuDNN, out of scope) wrapped like core/inference.py:35-37 and
+`rmnet_b200.install()` deployed behind them (RMNet.forward = the fused GPU-resident frame loop).  Workload: 8 clips per
+GPU shaped like BASELINE configs[2]/[4] (480x854, 5 objects, F = 60, memorize_every = 5), sharded clip-parallel over
+the ranks longest-first, one NCCL gather of the uint8 label maps (core/inference.py:61) at the end.  On rank 0 at N = 1
+the `vos` object adds: one F = 100 clip (memory reaches T = 20) with the frames/s of its T >= 20 tail, the unmodified
+reference (its own forward + its own CUDA extension) on the SAME GPU and clip, and the per-module device-time split.
+`e2e_op` is round 1's op-level end-to-end number (host k4/v4/q tensors in, mem_val out per step).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference]
+Extra legs on rank 0 at N = 1: the step replayed as a CUDA graph, the reference's own composition of the step on the same
+GPU (torch CUDA ops + its unmodified CUDA kernel), the attention kernel alone (roofline), the CPU baseline.
+
+`--impl reference`: the reference on the host cores -- `value` = the same hot-path step by the reference's own functions
+(MemoryReader / RMNet.warp / RMNet.get_att_map from baseline/_ref on torch CPU; the CUDA-only generator through the C
+oracle), `e2e` = VOS frames/sec of the unmodified tflownet + rmnet on a bounded sample clip.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4] [--impl ours|reference] [--precision split3|single]
 """
 import argparse
 import json
@@ -143,6 +155,84 @@ def time_cpu(wl, pool, steps, warmup):
     return steps / dt, dt / steps * 1e3, out
 
 
+class RefCpuClip:
+    """The same step by the REFERENCE's own functions on torch's CPU backend (imported from baseline/_ref, the shipped
+    copy of the reference tree): models/rmnet.py MemoryReader.forward (:147-165), RMNet.warp (:252-278), RMNet.get_att_map
+    (:280-287), utils.helpers.pad_divide_by; the three inline lines of memorize / segment that connect them (:245-248,
+    :356-358) restated; the CUDA-only generator extension replaced by the C oracle (baseline.cpu_generator_class)."""
+
+    def __init__(self, wl, pool):
+        import types
+        import torch
+        import baseline
+        self.torch, self.wl, self.pool = torch, wl, pool
+        ref = baseline.import_reference()
+        import utils.helpers as ref_helpers
+        self.helpers = ref_helpers
+        self.reader = ref.MemoryReader()
+        ns = types.SimpleNamespace(att_map_generator=baseline.cpu_generator_class()())
+        ns.warp = lambda img0, flow: ref.RMNet.warp(ns, img0, flow)
+        self.get_att_map = lambda prev_mask, flow=None: ref.RMNet.get_att_map(ns, prev_mask, flow)
+        n, T = wl["n"], wl["T"]
+        self.keys, self.vals = [], []
+        for t in range(T - 1):
+            k, v = self._masked_memory(pool["frames"][t])
+            self.keys.append(k)
+            self.vals.append(v)
+
+    def _t(self, a):
+        return self.torch.from_numpy(np.ascontiguousarray(a))
+
+    def _masked_memory(self, fr):
+        torch, n, H, W = self.torch, self.wl["n"], self.wl["H"], self.wl["W"]
+        (masks,), _ = self.helpers.pad_divide_by([self._t(fr["mask"])[None]], 16, (H, W))          # :212
+        att, _ = self.get_att_map(masks)                                                          # :244
+        a16 = torch.nn.functional.interpolate(att, scale_factor=1 / 16)[0, 1:n + 1, None]         # :245
+        return self._t(fr["k4"]) * a16, self._t(fr["v4"]) * a16                                   # :247-248
+
+    def step(self, i):
+        torch, n, T, H, W = self.torch, self.wl["n"], self.wl["T"], self.wl["H"], self.wl["W"]
+        fr = self.pool["frames"][T - 1 + i % (len(self.pool["frames"]) - T + 1)]
+        k_t, v_t = self._masked_memory(fr)
+        m_key = torch.stack(self.keys + [k_t], 2)                                                 # :416-421
+        m_val = torch.stack(self.vals + [v_t], 2)
+        att, _ = self.get_att_map(self._t(fr["mask"])[None], self._t(fr["flow"])[None])           # :431
+        (att,), _ = self.helpers.pad_divide_by([att], 16, (H, W))                                 # :307
+        a16 = torch.nn.functional.interpolate(att[0, 1:n + 1, None], scale_factor=1 / 16)         # :330, :356
+        k4e = self._t(fr["qk"])[None].expand(n, -1, -1, -1) * a16                                 # :357
+        v4e = self._t(fr["qv"])[None].expand(n, -1, -1, -1) * a16                                 # :358
+        mem_val, _ = self.reader(m_key.contiguous(), m_val.contiguous(), k4e, v4e)                # :361
+        return mem_val.numpy()
+
+
+def time_cpu_arm(wl, pool, steps, warmup, budget_s=90.0):
+    """-> (frames/s, ms/step, steps actually timed, kind, description).  kind "reference" = RefCpuClip (the reference's
+    own functions from baseline/_ref on torch CPU); "port" = the numpy/C oracle when the reference tree is not there."""
+    import baseline
+    cores = os.cpu_count() or 1
+    if baseline.available():
+        import torch
+        from baseline import vos
+        vos.set_host_threads()
+        with torch.no_grad():
+            clip = RefCpuClip(wl, pool)
+            for i in range(warmup):
+                clip.step(i)
+            t0 = time.perf_counter()
+            done = 0
+            for i in range(steps):
+                clip.step(i)
+                done += 1
+                if time.perf_counter() - t0 > budget_s:
+                    break
+            dt = time.perf_counter() - t0
+        return done / dt, dt / done * 1e3, done, "reference", (
+            f"{done} steps of the same workload by the reference's own MemoryReader / RMNet.warp / RMNet.get_att_map (baseline/_ref, "
+            f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads; generator = C oracle, the reference's is CUDA-only)")
+    fps, ms, _ = time_cpu(wl, pool, steps, warmup)
+    return fps, ms, steps, "port", f"{steps} steps of the same workload (oracle/: C generator + warp, numpy-BLAS MemoryReader on {cores} threads)"
+
+
 def cpu_model():
     try:
         for line in open("/proc/cpuinfo"):
@@ -225,6 +315,185 @@ def shard_clips(n_clips, rank, world):
     return [i for i in range(n_clips) if i % world == rank]
 
 
+def shard_longest_first(costs, world):
+    """Clip-parallel sharding, longest first: clips sorted by cost (F * n), each given to the least loaded
+    rank so far (ties -> lowest rank).  -> list of `world` lists of clip indices."""
+    shards, load = [[] for _ in range(world)], [0.0] * world
+    for i in sorted(range(len(costs)), key=lambda j: (-costs[j], j)):
+        r = min(range(world), key=lambda q: (load[q], q))
+        shards[r].append(i)
+        load[r] += costs[i]
+    return shards
+
+
+def gather_label_maps(stack, rank, world):
+    """One gather of every rank's uint8 label maps [clips, F, H, W] to rank 0 (core/inference.py:61 keeps exactly these):
+    NCCL on the GPU box, gloo in the CPU tests.  -> list of `world` tensors on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return [stack]
+    outs = [torch.empty_like(stack) for _ in range(world)] if rank == 0 else None
+    dist.gather(stack, outs, dst=0)
+    return outs
+
+
+def pin_rank_to_cores(local_rank, local_world):
+    """Give each rank its own slice of the host cores (the ranks of one node otherwise migrate over all of them and
+    contend for the same caches while staging pageable copies).  Returns the slice, or None when not applicable."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if local_world <= 1 or len(cores) < 2 * local_world:
+            return None
+        per = len(cores) // local_world
+        mine = cores[local_rank * per:(local_rank + 1) * per]
+        os.sched_setaffinity(0, mine)
+        return mine
+    except (AttributeError, OSError):
+        return None
+
+
+VOS_CLIPS_PER_GPU = 8
+VOS_SHAPE = dict(H=480, W=854, n=5, F=60, every=5)      # BASELINE configs[2]/[4] frame shape, the target's 5 objects
+VOS_LONG = dict(H=480, W=854, n=5, F=100, every=5)      # memory reaches T = 20 at frame 92 (SURVEY 3.1)
+
+
+def run_vos(args, rank, world, local_rank, dev, precision):
+    """The e2e leg: VOS frames/sec through the reference-facing API (see the module docstring).
+    -> (seconds of this rank's timed calls [+ gather], frames segmented by this rank, info dict)."""
+    import torch
+    import baseline
+    from baseline import vos
+    import rmnet_b200
+    ref = baseline.import_reference()
+    vos.reference_flags()
+    tfn, net = baseline.build_nets(0, dev, cpu_generator=False)
+    tfn_dp, net_dp = vos.wrap(tfn, net, [local_rank])                                 # core/inference.py:35-37
+    rmnet_b200.install(ref, precision=precision)
+    H, W, n, F_, every = (VOS_SHAPE[k] for k in ("H", "W", "n", "F", "every"))
+    n_clips = VOS_CLIPS_PER_GPU * world
+    clips = [dict(seed=5000 + i, n=n, F=F_) for i in range(n_clips)]
+    mine = shard_longest_first([c["F"] * c["n"] for c in clips], world)[rank]
+    L = rmnet_b200.lib()
+
+    def host_clip(c):
+        frames, masks, n_objects = baseline.synthetic_clip(c["seed"], c["n"], c["F"], H, W)
+        return frames, masks, n_objects                                               # pageable host tensors, int32 masks (utils/helpers.py:52-53)
+
+    def labels_of(probs):
+        lab = probs[0].argmax(1).to(torch.uint8)                                      # core/inference.py:61
+        return lab if lab.is_cuda else lab.to(dev)
+
+    # warm-up: one short clip of the same shape (cuDNN plans, graph capture of the frame body)
+    wf, wm, wn = baseline.synthetic_clip(4999, n, 8, H, W)
+    vos.run_clip(tfn_dp, net_dp, wf, wm, wn, every)
+    loop = net.__dict__["_rmnet_b200_loop"]
+    L.rmnet_launch_count_reset()
+    g0 = loop.graph_launches
+    secs, frames_done, labs, flow_s = 0.0, 0, [], 0.0
+    h2d = d2h = 0
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    for ci in mine:
+        frames, masks, n_objects = host_clip(clips[ci])
+        probs, s, sf = vos.run_clip(tfn_dp, net_dp, frames, masks, n_objects, every)
+        t0 = time.perf_counter()
+        lab = labels_of(probs)                                                        # the result the driver keeps (uint8 label maps)
+        lab_host = lab.cpu()
+        secs += s + (time.perf_counter() - t0)
+        flow_s += sf
+        frames_done += c_frames(clips[ci])
+        labs.append(lab)
+        # bytes crossing PCIe, counted from the tensors: DataParallel scatters every tensor argument of both calls (frames
+        # twice), the flows come back when the reference's rule keeps them on the host, est_masks / the label maps go back
+        flows_on_host = not (torch.cuda.device_count() > 1)
+        h2d += 2 * frames.numel() * 4 + masks.numel() * 4 + (frames.shape[1] * 2 * H * W * 4 if flows_on_host else 0)
+        d2h += (frames.shape[1] * 2 * H * W * 4 if flows_on_host else 0) + (probs.numel() * 4 if not probs.is_cuda else lab_host.numel())
+        del frames, masks, probs
+    launches = int(L.rmnet_launch_count()) + loop.graph_launches - g0
+    gather_s = 0.0
+    gathered = None
+    if world > 1:
+        import torch.distributed as dist
+        stack = torch.stack(labs)                                                     # [clips, F, H, W] uint8
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        outs = gather_label_maps(stack, rank, world)                                  # the one collective of the job
+        torch.cuda.synchronize()
+        gather_s = time.perf_counter() - t0
+        secs += gather_s
+        if rank == 0:
+            gathered = [int(o.numel()) for o in outs]
+    info = {"clips_total": n_clips, "clips_this_rank": len(mine), "frames_per_clip": F_, "objects": n, "memorize_every": every,
+            "flownet_share": flow_s / max(secs, 1e-9), "gather_s": gather_s, "gathered_label_bytes": gathered,
+            "launches": launches, "h2d_bytes_per_frame": h2d / max(frames_done, 1), "d2h_bytes_per_frame": d2h / max(frames_done, 1),
+            "allow_tf32_convs": bool(torch.backends.cudnn.allow_tf32), "graph": bool(loop.use_graph),
+            "label_checksum": float(sum(float(l.sum()) for l in labs))}
+
+    extra = None
+    if world == 1 and rank == 0 and not args.no_vos_extras:
+        extra = vos_extras(ref, tfn, net, tfn_dp, net_dp, dev, precision)
+    rmnet_b200.uninstall(ref)
+    return secs, frames_done, info, extra
+
+
+def c_frames(c):
+    return c["F"] - 1
+
+
+def vos_extras(ref, tfn, net, tfn_dp, net_dp, dev, precision):
+    """Rank 0 at N = 1: the F = 100 clip whose memory reaches T = 20 (north_star's target shape) -- ours, then the
+    UNMODIFIED reference (its own forward, its own CUDA extension from oracle/_ref) on the same GPU and clip -- and the
+    per-module device-time split of one frame."""
+    import torch
+    import baseline
+    from baseline import vos
+    import rmnet_b200
+    H, W, n, F_, every = (VOS_LONG[k] for k in ("H", "W", "n", "F", "every"))
+    out = {"clip": f"{H}x{W}, {n} objects, F={F_}, memorize_every={every} (T reaches 20 at frame 92)", "target_fps": 30.0}
+    frames, masks, n_objects = baseline.synthetic_clip(7000, n, F_, H, W)
+    loop = net.__dict__["_rmnet_b200_loop"]
+    loop.record_frame_times = True
+    try:
+        vos.run_clip(tfn_dp, net_dp, frames[:, :8], masks[:, :8], n_objects[:, :8], every)
+        probs, s, sf = vos.run_clip(tfn_dp, net_dp, frames, masks, n_objects, every)
+    finally:
+        loop.record_frame_times = False
+    ms = loop.last_frame_ms
+    tail = ms[91:]                                                                    # frames t >= 92: T >= 20
+    out["ours"] = {"fps": (F_ - 1) / s, "seconds": s, "flownet_seconds": sf,
+                   "rmnet_frame_ms_median": float(np.median(ms)), "rmnet_frame_ms_at_T20": float(np.mean(tail)),
+                   "rmnet_only_fps_at_T20": 1e3 / float(np.mean(tail)), "meets_target": (F_ - 1) / s >= 30.0}
+    lab = probs[0].argmax(1).cpu()
+    del probs
+    try:
+        baseline.import_reference(need_cuda_extension=True)
+        import reg_att_map_generator as ext
+        if "oracle" not in (getattr(ext, "__file__", "") or ""):
+            raise RuntimeError("the reference CUDA extension (oracle/_ref) is not the module `reg_att_map_generator` resolves to")
+        rmnet_b200.uninstall(ref)
+        vos.run_clip(tfn_dp, net_dp, frames[:, :4], masks[:, :4], n_objects[:, :4], every)
+        probs_r, s_r, sf_r = vos.run_clip(tfn_dp, net_dp, frames, masks, n_objects, every)
+        lab_r = probs_r[0].argmax(1).cpu()
+        out["reference_on_this_gpu"] = {"fps": (F_ - 1) / s_r, "seconds": s_r, "flownet_seconds": sf_r,
+                                        "what": "unmodified models/rmnet.py + models/tiny_flownet.py (baseline/_ref) + the unmodified reference CUDA extension "
+                                                "(oracle/_ref), same GPU, same clip, same two calls",
+                                        "label_agreement_free_running": float((lab == lab_r).float().mean())}
+        out["speedup_vs_reference_on_this_gpu"] = s_r / s
+        del probs_r
+    except Exception as e:
+        out["reference_on_this_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        rmnet_b200.install(ref, precision=precision)
+    try:
+        out["module_split_ms_at_T20"] = vos.module_split(net, tfn, H, W, n, 20, dev)
+    except Exception as e:
+        out["module_split_ms_at_T20"] = {"error": f"{type(e).__name__}: {e}"}
+    return out
+
+
 def reduce_over_ranks(dev_ms, e2e_s, checksum, device, rank, world):
     """Timing = MAX over ranks (all_reduce), results = one gather of per-rank checksums to rank 0.
     Works with NCCL (device = cuda) and with gloo (device = cpu, used by the CPU tests)."""
@@ -253,6 +522,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     from rmnet_b200 import ops
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    core_slice = pin_rank_to_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))   # before any pinned allocation
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -500,12 +770,44 @@ def run_gpu(args, wl, rank, world, local_rank):
         except Exception as e:
             ref_gpu = {"unavailable": f"{type(e).__name__}: {e}"}
 
-    # ---- max over ranks, trivial NCCL gather of a result checksum (north_star: "NCCL only for the result gather")
+    # ---- the e2e leg: VOS frames/sec through the reference-facing API, clips sharded over the ranks (run_vos)
+    del dflat, dbuf, obuf, flush
+    torch.cuda.empty_cache()
+    vos_s, vos_frames, vos_info, vos_extra = None, 0, None, None
+    if not args.no_vos:
+        try:
+            vos_s, vos_frames, vos_info, vos_extra = run_vos(args, rank, world, local_rank, dev, precision)
+        except Exception as e:
+            if world > 1:
+                raise
+            import traceback
+            vos_info = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1200:]}
+
+    # ---- max over ranks (device time, op-level e2e time, VOS time); sum of the frames segmented; checksums gathered
     checksum = float(m4.double().sum().item())
     dev_ms, e2e_s, sums = reduce_over_ranks(dev_ms, e2e_s, checksum, dev, rank, world)
+    vos_max_s, vos_total_frames = vos_s, vos_frames
+    if world > 1 and vos_s is not None:
+        import torch.distributed as dist
+        t = torch.tensor([vos_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        f = torch.tensor([vos_frames], device=dev, dtype=torch.float64)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+        vos_max_s, vos_total_frames = float(t[0]), int(f[0])
     if rank != 0:
         return None
     fps = world * args.steps / (dev_ms * 1e-3)
+    e2e_op = {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+              "what": "op-level: one pinned host staging buffer per frame (mask channels 1..n, flow, k4, v4, q_key, q_val) -> one H2D copy -> "
+                      "RegionalMemory.step -> D2H of mem_val every step; copies double-buffered on side streams"}
+    if vos_s is not None:
+        e2e = {"value": vos_total_frames / vos_max_s, "unit": "frames/s", "h2d_bytes_per_step": vos_info["h2d_bytes_per_frame"],
+               "d2h_bytes_per_step": vos_info["d2h_bytes_per_frame"], "frames": vos_total_frames, "seconds_max_over_ranks": vos_max_s,
+               "what": "VOS frames/sec through the reference-facing API: tflownet(frames) + rmnet(frames, masks, flows, n_objects, 5) "
+                       "(utils/helpers.py:55-56) on host tensors, unmodified reference nets wrapped like core/inference.py:35-37, "
+                       "rmnet_b200.install() behind them; a step = one segmented frame", **{k: v for k, v in vos_info.items() if k not in ("h2d_bytes_per_frame", "d2h_bytes_per_frame")}}
+    else:
+        e2e = dict(e2e_op, note="VOS leg not run: " + str(vos_info))
     line = {
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
@@ -514,11 +816,12 @@ def run_gpu(args, wl, rank, world, local_rank):
         "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path "
                                "(both region descriptors -> pack-at-memorise + query side -> tcgen05 regional read of all objects -> merge; "
                                "4 kernels chained by programmatic dependent launch: RegionalMemory.step)",
-                   "clips_per_gpu": 1, "parallelism": f"clip-parallel x{world} (no data-path collective)", "precision": args.precision,
+                   "clips_per_gpu": 1, "parallelism": f"clip-parallel x{world} (no data-path collective; one NCCL gather of the label maps in the e2e leg)",
+                   "precision": args.precision,
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed", "pool_frames": POOL,
-                   "e2e_mode": "one pinned host staging buffer per frame (mask channels 1..n, flow, k4, v4, q_key, q_val) -> one H2D copy -> "
-                               "RegionalMemory.step -> D2H of mem_val every step; copies double-buffered on side streams"},
-        "e2e": {"value": world * args.steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                   "e2e_workload": f"{VOS_CLIPS_PER_GPU} clips per GPU, {VOS_SHAPE['H']}x{VOS_SHAPE['W']}, {VOS_SHAPE['n']} objects, F={VOS_SHAPE['F']}, "
+                                   f"memorize_every={VOS_SHAPE['every']}, K={K_CH}; sharded longest-first, each rank pinned to its own host cores ({core_slice})"},
+        "e2e": e2e, "e2e_op": e2e_op, "vos": vos_extra,
         "gpu_launches": launches, "cuda_graph": graph_info, "reference_on_this_gpu": ref_gpu, "roofline": roof, "clocks": clk, "result_checksums": sums,
     }
     return line, pool
@@ -535,6 +838,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="split3", choices=["split3", "single"])
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto, ~10-30 s)")
+    ap.add_argument("--no-vos", action="store_true", help="skip the VOS e2e leg (op-level legs only)")
+    ap.add_argument("--no-vos-extras", action="store_true", help="skip the F=100 clip / reference-on-this-GPU / module split")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -542,22 +847,27 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        # The reference's own implementation of this path on the host cores.  MemoryReader / warp are Python (torch)
-        # and the tree does not travel to the GPU box, so this is the oracle port (numpy-BLAS + C), all host threads.
+        # The reference's own implementation on the host cores (all of them), rank 0 only.
         if rank != 0:
             return
         pool = make_pool(wl, 1234, 4)
-        steps = min(args.steps, {"c2": 20, "c3": 8}.get(args.workload, 1))
-        fps, ms, _ = time_cpu(wl, pool, steps, min(args.warmup, 2))
+        warm = min(args.warmup, 2)
+        fps, ms, steps, kind, sample = time_cpu_arm(wl, pool, args.steps, warm)
         cores = os.cpu_count()
+        vos_cpu = cpu_vos_sample()
+        e2e = {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        if "fps" in vos_cpu:
+            e2e = {"value": vos_cpu["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                   "what": "VOS frames/sec of the unmodified tflownet + rmnet on the host cores -- the counterpart of the GPU arm's e2e "
+                           "(`value` is the counterpart of the GPU arm's `value`: the hot-path step alone)", **vos_cpu}
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 2), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path", "device": "host CPU"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-                             "sample": f"{steps} steps of the same workload (oracle/: C generator + warp, numpy-BLAS MemoryReader on {cores} threads)"},
-            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path", "device": "host CPU",
+                       "steps_requested": args.steps, "note": "steps are cut at a 90 s budget"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "cpu": cpu_model(), "sample": sample},
+            "e2e": e2e}))
         return
 
     if world > 1:
@@ -570,14 +880,39 @@ def main():
         line, pool = res
         if world == 1:
             steps = args.cpu_steps or {"c2": 20, "c3": 10}.get(args.workload, 1)
-            fps, ms, _ = time_cpu(wl, make_pool(wl, 1234, 4), steps, 1)
-            cores = os.cpu_count()
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "cpu": cpu_model(), "ms_per_step": ms,
-                                    "sample": f"{steps} steps of the same workload on the host (oracle/: C generator + warp, numpy-BLAS MemoryReader, {cores} threads)"}
+            fps, ms, steps, kind, sample = time_cpu_arm(wl, make_pool(wl, 1234, 4), steps, 1, budget_s=30.0)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": kind, "cpu": cpu_model(), "ms_per_step": ms,
+                                    "sample": sample, "vos": None if args.no_vos else cpu_vos_sample()}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def cpu_vos_sample(n_frames=3):
+    """VOS frames/sec of the UNMODIFIED reference (tflownet + rmnet from baseline/_ref, torch CPU, all host threads; the
+    CUDA-only generator replaced by the C oracle) on a bounded sample: the first `n_frames` frames of an e2e-leg clip."""
+    try:
+        import torch
+        import baseline
+        from baseline import vos
+        if not baseline.available():
+            return {"unavailable": "baseline/_ref not populated"}
+        threads = vos.set_host_threads()
+        H, W, n, every = (VOS_SHAPE[k] for k in ("H", "W", "n", "every"))
+        tfn, net = baseline.build_nets(0, "cpu", cpu_generator=True)
+        frames, masks, n_objects = baseline.synthetic_clip(5000, n, n_frames, H, W)
+        cuda_was = torch.cuda.is_available
+        torch.cuda.is_available = lambda: False          # utils/helpers.py:18 var_or_cuda would move tensors to the GPU of the box
+        try:
+            _, s, sf = vos.run_clip(tfn, net, frames, masks, n_objects, every)
+        finally:
+            torch.cuda.is_available = cuda_was
+        return {"fps": (n_frames - 1) / s, "seconds": s, "flownet_seconds": sf, "cores": threads, "kind": "reference",
+                "sample": f"first {n_frames} frames ({n_frames - 1} segmented) of a {H}x{W}, {n}-object clip; unmodified models/rmnet.py + "
+                          f"models/tiny_flownet.py on torch CPU, {threads} threads"}
+    except Exception as e:
+        return {"unavailable": f"{type(e).__name__}: {e}"}
 
 
 if __name__ == "__main__":

@@ -164,7 +164,15 @@ RMNET_API int rmnet_bank_memorize(void *bank, size_t bank_bytes, int n_slots, in
                         long long v_obj_stride, long long v_ch_stride, const int *rects, int n_obj,
                         int h, int w, int elem_format, int commit, void *stream);
 /* Host-visible copy of the per-slot counters (synchronises `stream`): out_host [n_slots,8] i32 =
- * (cells_committed, cells_temp, zeros_committed, zeros_temp, frames_committed, frames_temp, 0, 0). */
+ * (cells_committed, cells_temp, zeros_committed, zeros_temp, frames_committed, frames_temp, overflow, range).
+ * Capacity: a memorize whose in-region cells do not fit behind the committed ones (cells_committed + r > cap_cells)
+ * stores NOTHING for that slot (the frame then counts as fully masked) and sets the slot's sticky `overflow` flag, which
+ * only rmnet_bank_reset clears.  The kernels cannot report that through a return code (they run asynchronously), so a
+ * direct C caller must size cap_cells for the frames it commits or poll this function: it fills out_host and returns
+ * RMNET_E_WORKSPACE when any slot has overflowed.
+ * Range: elem_format 1 (fp16 hi/lo planes, 22 mantissa bits -- the default of the Python layer) represents |x| <= 65504;
+ * a key / value / query key beyond that is stored saturated and sets the sticky `range` flag (-> RMNET_E_UNSUPPORTED
+ * here).  elem_format 0 (bf16 planes, 16 mantissa bits) has fp32's range. */
 RMNET_API int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells, int *out_host, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -250,9 +258,14 @@ RMNET_API int rmnet_memory_reader_forward(const float *m_key, const float *m_val
  *   out [H,W,2] f32.  Bit-exact with the reference's -O2 (no-FMA) build.
  *   The *_host variant takes HOST arrays (what the NumPy-facing module passes), stages them through
  *   `dev_scratch` (>= 2*H*W*2*4 bytes of device memory) and synchronises before returning.
+ *   The *_cpu variant is the same arithmetic in plain host C (no CUDA call at all; compiled with
+ *   -ffp-contract=off): the reference calls this op inside forked DataLoader worker processes
+ *   (utils/data_transforms.py:293-302), where a CUDA context cannot be created.  All pointers are HOST.
  * ------------------------------------------------------------------------------------------- */
 RMNET_API int rmnet_update_optical_flow(const float *of, const float *m1_host, const float *m2_host, int H, int W,
                               float *out, void *stream);
+RMNET_API int rmnet_update_optical_flow_cpu(const float *of_host, const float *m1_host, const float *m2_host, int H, int W,
+                                  float *out_host);
 RMNET_API int rmnet_update_optical_flow_host(const float *of_host, const float *m1_host, const float *m2_host,
                                    int H, int W, float *out_host, void *dev_scratch,
                                    size_t dev_scratch_bytes, void *stream);

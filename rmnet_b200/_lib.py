@@ -58,6 +58,7 @@ PROTOTYPES = {
     "rmnet_memory_reader_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                             c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "rmnet_update_optical_flow": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "rmnet_update_optical_flow_cpu": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "rmnet_update_optical_flow_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
                                                c_size_t, c_void_p]),
 }

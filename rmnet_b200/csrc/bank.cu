@@ -36,7 +36,7 @@ struct PackSmem {
 //   it 16 B at a time: chunk j of the 32 rows is stored contiguously ([group][16 chunks][32 rows][8 ch]) so that
 //   every such warp load is one coalesced 512 B access.  dst_* point at the first row of a 32-aligned group.
 template <int FMT, bool INTERLEAVED>
-__device__ __forceinline__ void pack_key_rows(PackSmem &sm, const float *__restrict__ src, long long ch_stride, const int4 rect,
+__device__ __forceinline__ bool pack_key_rows(PackSmem &sm, const float *__restrict__ src, long long ch_stride, const int4 rect,
                                               int w, int i0, int cnt, int rows, uint16_t *__restrict__ dst_hi,
                                               uint16_t *__restrict__ dst_lo) {
   const int li = threadIdx.x & (kCellsPerCta - 1);  // cell within the tile
@@ -46,14 +46,15 @@ __device__ __forceinline__ void pack_key_rows(PackSmem &sm, const float *__restr
   float x[kPerThread];
 #pragma unroll
   for (int k = 0; k < kPerThread; ++k) x[k] = live ? __ldg(kp + (long long)(cg + kGroups * k) * ch_stride) : 0.f;
+  bool sat = false;
 #pragma unroll
   for (int k = 0; k < kPerThread; ++k) {
     uint16_t hi, lo;
-    split16(x[k], FMT, hi, lo);
+    sat |= split16(x[k], FMT, hi, lo);
     sm.hi[li][cg + kGroups * k] = hi;
     sm.lo[li][cg + kGroups * k] = lo;
   }
-  __syncthreads();
+  sat = FMT == 1 ? (__syncthreads_or(sat) != 0) : (__syncthreads(), false);
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   if (INTERLEAVED) {
     // warp `wrp` writes chunks 2*wrp, 2*wrp + 1 of both 32-row groups of the tile; lane = row within the group
@@ -75,6 +76,7 @@ __device__ __forceinline__ void pack_key_rows(PackSmem &sm, const float *__restr
       *reinterpret_cast<uint2 *>(dst_lo + g) = *reinterpret_cast<const uint2 *>(&sm.lo[row][lane * 4]);
     }
   }
+  return sat;
 }
 
 template <int FMT>
@@ -100,8 +102,9 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
       if (i0 >= r_pad) return;
       const size_t row0 = ((size_t)o * qs.nq_pad + i0) * RMNET_CK;
       // r_pad is a multiple of 128: the tile's 64 rows are two whole 32-row groups
-      pack_key_rows<FMT, true>(sm, qs.q_key + (long long)o * qs.q_key_obj_stride, (long long)N, qrect, w, i0,
-                               max(0, min(kCellsPerCta, r - i0)), kCellsPerCta, qs.qhi + row0, qs.qlo + row0);
+      const bool sat = pack_key_rows<FMT, true>(sm, qs.q_key + (long long)o * qs.q_key_obj_stride, (long long)N, qrect, w, i0,
+                                                max(0, min(kCellsPerCta, r - i0)), kCellsPerCta, qs.qhi + row0, qs.qlo + row0);
+      if (sat && qs.range_flag && threadIdx.x == 0) atomicOr(qs.range_flag, 1);
       return;
     }
     // ---- q_val passthrough (v4e * att16 into channels 512..1023 of mem_val, :358 + :163): 64 cells x 128 channels.
@@ -157,7 +160,9 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
 
   if (role == ROLE_MEM_KEYS) {
     const size_t row0 = ((size_t)o * bank.cap + base + i0) * RMNET_CK;
-    pack_key_rows<FMT, false>(sm, k4 + (long long)o * k_obj_stride, k_ch_stride, rect, w, i0, cnt, cnt, bank.khi + row0, bank.klo + row0);
+    if (pack_key_rows<FMT, false>(sm, k4 + (long long)o * k_obj_stride, k_ch_stride, rect, w, i0, cnt, cnt, bank.khi + row0, bank.klo + row0) &&
+        threadIdx.x == 0)
+      atomicOr(meta + META_RANGE, 1);
     return;
   }
 
@@ -174,16 +179,18 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
   float x[kPerThread];
 #pragma unroll
   for (int k = 0; k < kPerThread; ++k) x[k] = live ? __ldg(vp + (long long)(cbase + cg + kGroups * k) * v_ch_stride) : 0.f;
+  bool sat = false;
 #pragma unroll
   for (int k = 0; k < kPerThread; ++k) {
     if (live) {
       const int c = cbase + cg + kGroups * k;
       uint16_t hi, lo;
-      split16(x[k], FMT, hi, lo);
+      sat |= split16(x[k], FMT, hi, lo);
       bank.vhi[vrow0 + (size_t)c * bank.cap] = hi;
       bank.vlo[vrow0 + (size_t)c * bank.cap] = lo;
     }
   }
+  if (FMT == 1 && sat) atomicOr(meta + META_RANGE, 1);   // (never taken for in-range features)
   // Per-channel sums over the warp's 32 cells by a transpose-reduction: in step s every lane keeps half of its values
   // and adds the partner's copy of the same half (31 shuffles instead of 32 x 5); lane l ends up with the total of its
   // l-th channel.  Dead lanes hold zeros.
@@ -309,6 +316,17 @@ int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells, int *out
   RMNET_CUDA(cudaMemcpyAsync(out_host, (const char *)bank + L.off_meta, (size_t)n_slots * 8 * sizeof(int),
                              cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   RMNET_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (int s = 0; s < n_slots; ++s)
+    if (out_host[s * 8 + META_RANGE]) {
+      set_error("fp16 planes saturated: slot %d stored a key / value (or packed a query key) beyond +-65504; use elem_format 0 (bf16 planes)", s);
+      return RMNET_E_UNSUPPORTED;
+    }
+  for (int s = 0; s < n_slots; ++s)
+    if (out_host[s * 8 + META_OVERFLOW]) {
+      set_error("memory bank overflow: slot %d dropped a frame (cap_cells = %d, %d committed cells)", s, cap_cells,
+                out_host[s * 8 + META_CELLS_C]);
+      return RMNET_E_WORKSPACE;
+    }
   return RMNET_OK;
 }
 }

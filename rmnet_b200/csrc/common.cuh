@@ -85,6 +85,7 @@ struct QuerySide {
   int nq_pad;
   int vec4;                                      // 128-bit accesses allowed for q_val / mem_val
   float *mem_val;
+  int *range_flag;                               // optional: set to 1 when a query key saturated the fp16 planes (bank meta, slot 0)
 };
 int bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *k4, long long k_obj_stride,
                        long long k_ch_stride, const float *v4, long long v_obj_stride, long long v_ch_stride, const int *rects,
@@ -118,7 +119,7 @@ static inline BankLayout bank_layout(int n_slots, int cap) {
   return L;
 }
 // meta ints per slot
-enum { META_CELLS_C = 0, META_CELLS_T = 1, META_ZEROS_C = 2, META_ZEROS_T = 3, META_FRAMES_C = 4, META_FRAMES_T = 5, META_OVERFLOW = 6 };
+enum { META_CELLS_C = 0, META_CELLS_T = 1, META_ZEROS_C = 2, META_ZEROS_T = 3, META_FRAMES_C = 4, META_FRAMES_T = 5, META_OVERFLOW = 6, META_RANGE = 7 };
 
 // Device view of a bank, passed by value to kernels.
 struct BankView {
@@ -201,8 +202,12 @@ static inline int pick_splits(int n_obj, int N, int q_tile, int cap) {
 }
 
 #ifdef __CUDACC__
-// 16-bit hi/lo split of an fp32 value.  fmt 0 = bf16, 1 = fp16.  x ~= hi + lo with |err| <= 2^-17|x| (bf16).
-__device__ __forceinline__ void split16(float x, int fmt, uint16_t &hi, uint16_t &lo) {
+// 16-bit hi/lo split of an fp32 value.  fmt 0 = bf16 (8 + 8 mantissa bits: |err| <= 2^-17 |x|, fp32's range),
+// fmt 1 = fp16 (11 + 11 bits: |err| <= 2^-23 |x| for |x| in [2^-3, 65504]; absolute error <= 2^-25 below that).
+// fp16 planes saturate at +-65504: the return value tells the caller that x was out of range (reported through the
+// bank's META_RANGE flag).  NaN passes through as NaN in both formats.
+__device__ __forceinline__ bool split16(float x, int fmt, uint16_t &hi, uint16_t &lo) {
+  bool sat = false;
   if (fmt == 0) {
     __nv_bfloat16 h = __float2bfloat16_rn(x);
     float r = x - __bfloat162float(h);
@@ -210,12 +215,15 @@ __device__ __forceinline__ void split16(float x, int fmt, uint16_t &hi, uint16_t
     hi = __bfloat16_as_ushort(h);
     lo = __bfloat16_as_ushort(l);
   } else {
+    sat = fabsf(x) > 65504.f;
+    if (sat) x = copysignf(65504.f, x);
     __half h = __float2half_rn(x);
     float r = x - __half2float(h);
     __half l = __float2half_rn(r);
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(l);
   }
+  return sat;
 }
 __device__ __forceinline__ float join16(uint16_t hi, uint16_t lo, int fmt) {
   if (fmt == 0) return __bfloat162float(__ushort_as_bfloat16(hi)) + __bfloat162float(__ushort_as_bfloat16(lo));

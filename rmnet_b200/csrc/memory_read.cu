@@ -20,8 +20,9 @@ __global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
 
 
 QuerySide make_query_side(const float *q_key, const float *q_val, long long q_key_obj_stride, const int *q_rects,
-                          const ReadWorkspace &W, int N, float *mem_val) {
+                          const ReadWorkspace &W, int N, float *mem_val, int *range_flag) {
   QuerySide qs;
+  qs.range_flag = range_flag;
   qs.q_key = q_key;
   qs.q_val = q_val;
   qs.q_key_obj_stride = q_key_obj_stride;
@@ -60,7 +61,7 @@ int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int 
   int rc = RMNET_OK;
   const bool umma = impl == RMNET_IMPL_UMMA;
   if (stages & RMNET_STAGE_QUERY) {  // (rmnet_frame_step folds this into its pack launch instead)
-    QuerySide qs = make_query_side(q_key, q_val, q_obj_stride, q_rects, W, h * w, mem_val);
+    QuerySide qs = make_query_side(q_key, q_val, q_obj_stride, q_rects, W, h * w, mem_val, bv.meta + META_RANGE);
     if ((rc = launch_query_side(qs, n_obj, h, w, elem_format, st))) return rc;
   }
   if (!(stages & RMNET_STAGE_PARTIAL)) {
@@ -120,7 +121,7 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   ReadWorkspace RW = rmnet::read_workspace(read_workspace, n_obj, (int)N, umma ? READ_MAX_SPLITS : pick_splits(n_obj, (int)N, 64, cap_cells));
   if (read_workspace_bytes < RW.total) { set_error("workspace too small: %zu < %zu", read_workspace_bytes, RW.total); return RMNET_E_WORKSPACE; }
   // the pack launch also prepares the query side (packed query keys, q_val passthrough) of this frame's read
-  QuerySide qs = make_query_side(q_key, q_val, 0, cur_rc + 4, RW, (int)N, mem_val);
+  QuerySide qs = make_query_side(q_key, q_val, 0, cur_rc + 4, RW, (int)N, mem_val, bv.meta + META_RANGE);
   rc = bank_memorize_impl(bank, bank_bytes, n_slots, cap_cells, k4, RMNET_CK * N, N, v4, RMNET_CV * N, N, mem_rc + 4, n_obj, h, w,
                           elem_format, commit, /*chained=*/true, &qs, stream);
   if (rc) return rc;
@@ -134,7 +135,7 @@ static size_t reader_scratch_layout(int n, int T, int h, int w, size_t *off_rect
   const int N = h * w;
   *cap = cdiv(T * N, 64) * 64;
   size_t o = align_up(bank_layout(n, *cap).total, 1024);
-  *off_rects = o; o = align_up(o + (size_t)n * 16, 1024);
+  *off_rects = o; o = align_up(o + (size_t)n * 32, 1024);
   *off_read = o; o += rmnet_memory_read_workspace_bytes(n, h, w, *cap);
   return o;
 }
@@ -158,18 +159,19 @@ int rmnet_memory_reader_forward(const float *m_key, const float *m_val, const fl
   const int N = h * w;
   char *ws = (char *)workspace;
   const size_t bank_bytes = bank_layout(n, cap).total;
-  int *rects = (int *)(ws + off_rects);
+  int *rects = (int *)(ws + off_rects);            // [n] query rectangles (dense h x w), then [n] memory rectangles
+  int *mem_rects = rects + 4 * n;
   int rc = rmnet_bank_reset(ws, bank_bytes, n, cap, stream);
   if (rc) return rc;
   fill_dense_rects_kernel<<<cdiv(n, 128), 128, 0, st>>>(rects, n, h, w);
+  fill_dense_rects_kernel<<<cdiv(n, 128), 128, 0, st>>>(mem_rects, n, T * h, w);
   RMNET_LAUNCH_CHECK();
-  // pack every memory frame (dense rectangle: the literal signature carries no region information)
-  for (int t = 0; t < T; ++t) {
-    rc = rmnet_bank_memorize(ws, bank_bytes, n, cap, m_key + (size_t)t * N, (long long)RMNET_CK * T * N, (long long)T * N,
-                             m_val + (size_t)t * N, (long long)RMNET_CV * T * N, (long long)T * N, rects, n, h, w,
-                             elem_format, /*commit=*/1, stream);
-    if (rc) return rc;
-  }
+  // ONE pack launch for the whole memory: [n,C,T,h,w] is a dense (T*h) x w cell grid with channel stride T*h*w (the
+  // literal signature carries no region information, so every cell is stored; position t*N + y*w + x, the reference's
+  // own flattening, :151)
+  rc = rmnet_bank_memorize(ws, bank_bytes, n, cap, m_key, (long long)RMNET_CK * T * N, (long long)T * N, m_val,
+                           (long long)RMNET_CV * T * N, (long long)T * N, mem_rects, n, T * h, w, elem_format, /*commit=*/1, stream);
+  if (rc) return rc;
   rc = rmnet_bank_memory_read(ws, bank_bytes, n, cap, q_key, q_val, (long long)RMNET_CK * N, rects, n, h, w, elem_format,
                               precision, impl, RMNET_STAGE_ALL, mem_val, ws + off_read, workspace_bytes - off_read, stream);
   if (rc || p == nullptr) return rc;

@@ -198,7 +198,17 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
                         const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
                         const int *__restrict__ q_rects, int h, int w,
                         float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
-                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg, int dbg_flags) {
+                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg_arg, int dbg_flags_arg) {
+  // Development instrumentation (S dump, clock64 stamps, the no-TMA experiment) exists only in -DRMNET_DEV builds
+  // (`make DEV=1`); in the release build the hooks are compile-time nulls and every branch on them is dead code.
+#ifdef RMNET_DEV
+  float *const dbg = dbg_arg;
+  const int dbg_flags = dbg_flags_arg;
+#else
+  constexpr float *dbg = nullptr;
+  constexpr int dbg_flags = 0;
+  (void)dbg_arg; (void)dbg_flags_arg;
+#endif
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -206,7 +216,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
   __shared__ SchedTable sched;
 
-  long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 16 : nullptr;  // dev hook
+#ifdef RMNET_DEV
+  long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 16 : nullptr;
+#else
+  constexpr long long *tstamp = nullptr;
+#endif
   if (tstamp && threadIdx.x == 128) tstamp[0] = clock64();
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
@@ -663,7 +677,10 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
 
 }  // namespace rmnet
 
-// development hook (not part of the public header): dump S of the first tile of CTA (0,0,0) into `ptr` (128*64 + 128 floats)
+#ifdef RMNET_DEV
+// development hooks, `make DEV=1` builds only (never in the release library, not part of the public header):
+// dump S of the first tile of CTA (0,0,0) into `ptr` (128*64 + 128 floats)
 extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_dump(float *ptr) { rmnet::g_dbg = ptr; }
 // development hook: bit 0 = the TMA producers stop loading after the first ring fill (timing experiment only: results are garbage)
 extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_flags(int flags) { rmnet::g_dbg_flags = flags; }
+#endif  // RMNET_DEV

@@ -25,7 +25,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import CH_ABSENT, CH_KEEP, CH_NEW, ELEM_BF16, RMNET_IMPL_AUTO, RMNET_PREC_SPLIT3, lib
+from ._lib import CH_ABSENT, CH_KEEP, CH_NEW, ELEM_FP16, RMNET_IMPL_AUTO, RMNET_PREC_SPLIT3, lib
 from .modules import RegionalMemory
 
 
@@ -92,13 +92,15 @@ class RegionalFrameLoop:
     more than one GPU is visible and no device is given, else a CPU tensor)."""
 
     def __init__(self, memorize_net, query_net, decoder_net, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                 elem_format=ELEM_BF16, use_graph=False, output="device"):
+                 elem_format=ELEM_FP16, use_graph=False, output="device", min_bank_frames=24):
         self.memorize_net, self.query_net, self.decoder_net = memorize_net, query_net, decoder_net
         self.precision, self.impl, self.elem_format = precision, impl, elem_format
         self.use_graph, self.output = bool(use_graph), output
+        self.min_bank_frames = int(min_bank_frames)   # bank capacity floor: 24 frames hold a 115-frame clip at memorize_every = 5
         self.last_bboxes = None   # [(prev_bbox, curr_bbox)] of the last clip (keep_bboxes=True), for inspection / tests
         self.last_logits = None   # [logit [1,K,H,W]] of the last clip (keep_logits=True): the return values of RMNet.segment + overrides
         self.last_frame_ms = None  # per-frame device time of the last clip (time_frames=True)
+        self.record_frame_times = False   # forward() records per-frame CUDA events into last_frame_ms (bench)
         self.graph_launches = 0    # kernels of this library launched through graph replays (rmnet_launch_count() only sees eager calls)
         self._states = {}
 
@@ -129,7 +131,7 @@ class RegionalFrameLoop:
         st = self._states.get(key)
         if st is None or st.max_frames < n_commits + 1:
             # capacity in whole multiples of 8 frames so that clips of similar length reuse the bank and its graphs
-            cap = ((n_commits + 1 + 7) // 8) * 8
+            cap = max(self.min_bank_frames, ((n_commits + 1 + 7) // 8) * 8)
             st = _ClipState(self, n, K, H, W, cap, dev)
             self._states[key] = st
         else:
@@ -208,7 +210,7 @@ class RegionalFrameLoop:
             out_mode = "device" if (torch.cuda.device_count() > 1 and device is None) else "host"
         with torch.cuda.device(dev):
             return self._run(frames, masks, optical_flows, n_objects, memorize_every, dev, n_frames, K, H, W, out_mode,
-                             teacher_masks, keep_logits, keep_bboxes, time_frames)
+                             teacher_masks, keep_logits, keep_bboxes, time_frames or self.record_frame_times)
 
     def _run(self, frames, masks, optical_flows, n_objects, memorize_every, dev, n_frames, K, H, W, out_mode, teacher_masks,
              keep_logits, keep_bboxes, time_frames):

@@ -11,7 +11,7 @@ so they drop in under core/inference.py.  Compute is exclus
 import torch
 
 from . import ops
-from ._lib import ELEM_BF16, RMNET_IMPL_AUTO, RMNET_PREC_SPLIT3
+from ._lib import ELEM_FP16, RMNET_IMPL_AUTO, RMNET_PREC_SPLIT3
 
 
 class RegionalAttentionMapGeneratorFunction(torch.autograd.Function):
@@ -42,7 +42,7 @@ class MemoryReader(torch.nn.Module):
     caller ignores it (`m4, viz = self.memory(...)`, models/rmnet.py:361), so by default None is returned in its place.
     `MemoryReader(return_p=True)` restores the reference's tuple (a separate fp32 kernel writes p)."""
 
-    def __init__(self, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16, return_p=False):
+    def __init__(self, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO, elem_format=ELEM_FP16, return_p=False):
         super().__init__()
         self.precision, self.impl, self.elem_format, self.return_p = precision, impl, elem_format, return_p
 
@@ -78,7 +78,7 @@ class RegionalMemory:
     """
 
     def __init__(self, n_objects, frame_hw, max_frames, device, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                 elem_format=ELEM_BF16, scan_all_channels=False):
+                 elem_format=ELEM_FP16, scan_all_channels=False):
         H, W = frame_hw
         self.lw, self.uw, self.lh, self.uh = ops.pad_amounts(H, W)
         self.Hp, self.Wp = H + self.lh + self.uh, W + self.lw + self.uw
@@ -131,15 +131,17 @@ class RegionalMemory:
             self._boxes = torch.empty((4, K, 4), dtype=torch.int32, device=dev)
         if out is None:
             out = torch.empty((self.n, 1024, self.h, self.w), dtype=torch.float32, device=dev)
-        if torch.cuda.current_device() != dev.index:
-            torch.cuda.set_device(dev)
         ws = self._box_ws
-        ops.check(ops.lib().rmnet_frame_step(
-            bank.ptr, bank.nbytes, bank.n_slots, bank.cap, prev_mask.data_ptr(), flow.data_ptr(), K, H, W,
-            ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, self.k_scan, k4.data_ptr(), v4.data_ptr(),
-            k4q.data_ptr(), v4q.data_ptr(), self.n, bank.elem_format, self.precision, self.impl, 1 if commit else 0,
-            self._boxes.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), bank._ws_ptr, bank._ws.numel() - 1024,
-            torch.cuda.current_stream(dev).cuda_stream), "frame_step")
+        with torch.cuda.device(dev):   # the caller's current device is left as it was
+            rc = ops.lib().rmnet_frame_step(
+                bank.ptr, bank.nbytes, bank.n_slots, bank.cap, prev_mask.data_ptr(), flow.data_ptr(), K, H, W,
+                ops.default_sampler(), 0.5, 10, 64, self.lw, self.uw, self.lh, self.uh, self.k_scan, k4.data_ptr(), v4.data_ptr(),
+                k4q.data_ptr(), v4q.data_ptr(), self.n, bank.elem_format, self.precision, self.impl, 1 if commit else 0,
+                self._boxes.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(), bank._ws_ptr, bank._ws.numel() - 1024,
+                torch.cuda.current_stream(dev).cuda_stream)
+            if rc != 0:
+                ws.zero_()     # the self-cleaning region workspace must be zero before the next launch, whatever happened
+            ops.check(rc, "frame_step")
         if commit:
             bank.frames_committed += 1
             bank.has_temp = False
@@ -217,7 +219,7 @@ def fused_forward(self, frames, masks, optical_flows, n_objects, memorize_every,
 
 
 def install(models_rmnet_module, fused=True, use_graph=None, output="reference", precision=RMNET_PREC_SPLIT3,
-            impl=RMNET_IMPL_AUTO, elem_format=ELEM_BF16):
+            impl=RMNET_IMPL_AUTO, elem_format=ELEM_FP16):
     """Rebind the reference's names so that an unmodified core/inference.py builds an RMNet that runs on this library
     (RMNet.__init__ looks the classes up at construction time, models/rmnet.py:187-189; core/inference.py:17 imports the
     RMNet class itself, so its methods are patched in place):

@@ -33,6 +33,17 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
+def _check_ws(rc, what, ws):
+    """check() for the launches that use a self-cleaning (zero-identity) workspace: a failed call may have left it dirty,
+    so it is re-zeroed before the error is raised."""
+    if rc != 0:
+        try:
+            ws.zero_()
+        except Exception:
+            pass
+    check(rc, what)
+
+
 def _zero_ws(dev, nbytes):
     """Self-cleaning generator workspace, one per (device, stream): zero-filled once."""
     key = (dev.index, _stream(dev))
@@ -53,10 +64,10 @@ def reg_att_map_forward(mask, prob_threshold=0.5, n_pts_threshold=10, n_bbox_loo
         att = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if want_att else None
         nws = lib().rmnet_reg_att_map_workspace_bytes(B, K)
         ws = _zero_ws(dev, nws)
-        check(lib().rmnet_reg_att_map_forward(mask.data_ptr(), B, K, H, W, float(prob_threshold), int(n_pts_threshold),
+        _check_ws(lib().rmnet_reg_att_map_forward(mask.data_ptr(), B, K, H, W, float(prob_threshold), int(n_pts_threshold),
                                               int(n_bbox_loose_pixels), bboxes.data_ptr(),
                                               att.data_ptr() if want_att else None, ws.data_ptr(), ws.numel(),
-                                              _stream(dev)), "reg_att_map_forward")
+                                              _stream(dev)), "reg_att_map_forward", ws)
     return [att, bboxes]
 
 
@@ -96,11 +107,11 @@ def warp_att_map_forward(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10
         bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
         att = torch.empty((B, K, H, W), dtype=torch.float32, device=dev) if want_att else None
         ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
-        check(lib().rmnet_warp_att_map_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
+        _check_ws(lib().rmnet_warp_att_map_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
                                                default_sampler() if sampler is None else sampler, float(prob_threshold),
                                                int(n_pts_threshold), int(n_bbox_loose_pixels), bboxes.data_ptr(),
                                                att.data_ptr() if want_att else None, ws.data_ptr(), ws.numel(),
-                                               _stream(dev)), "warp_att_map_forward")
+                                               _stream(dev)), "warp_att_map_forward", ws)
     return att, bboxes
 
 
@@ -122,11 +133,11 @@ def regional_boxes(mask, flow=None, padded_frame=True, prob_threshold=0.5, n_pts
         bboxes = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
         rects = torch.empty((B, K, 4), dtype=torch.int32, device=dev)
         ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
-        check(lib().rmnet_regional_boxes_forward(mask.data_ptr(), flow.data_ptr() if flow is not None else None, B, K, H, W,
+        _check_ws(lib().rmnet_regional_boxes_forward(mask.data_ptr(), flow.data_ptr() if flow is not None else None, B, K, H, W,
                                                  default_sampler() if sampler is None else sampler, float(prob_threshold),
                                                  int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh,
                                                  1 if padded_frame else 0, int(k_scan), bboxes.data_ptr(), rects.data_ptr(), ws.data_ptr(),
-                                                 ws.numel(), _stream(dev)), "regional_boxes_forward")
+                                                 ws.numel(), _stream(dev)), "regional_boxes_forward", ws)
     return bboxes, rects
 
 
@@ -143,11 +154,11 @@ def frame_regions(prev_mask, flow, prob_threshold=0.5, n_pts_threshold=10, n_bbo
     with torch.cuda.device(dev):
         out = torch.empty((4, B, K, 4), dtype=torch.int32, device=dev)
         ws = _zero_ws(dev, lib().rmnet_reg_att_map_workspace_bytes(B, K))
-        check(lib().rmnet_frame_regions_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
+        _check_ws(lib().rmnet_frame_regions_forward(prev_mask.data_ptr(), flow.data_ptr(), B, K, H, W,
                                                 default_sampler() if sampler is None else sampler, float(prob_threshold),
                                                 int(n_pts_threshold), int(n_bbox_loose_pixels), lw, uw, lh, uh, int(k_scan),
                                                 out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(),
-                                                ws.data_ptr(), ws.numel(), _stream(dev)), "frame_regions_forward")
+                                                ws.data_ptr(), ws.numel(), _stream(dev)), "frame_regions_forward", ws)
     return out[0], out[1], out[2], out[3]
 
 
@@ -209,7 +220,7 @@ class MemoryBank:
     """Preallocated region-compacted memory bank of one clip (replaces the reference's `keys`/`values` tensors
     and their per-frame torch.cat, models/rmnet.py:416-426).  Slot s holds object s+1."""
 
-    def __init__(self, n_slots, h, w, max_frames, device, elem_format=ELEM_BF16):
+    def __init__(self, n_slots, h, w, max_frames, device, elem_format=ELEM_FP16):
         self.n_slots, self.h, self.w = int(n_slots), int(h), int(w)
         self.max_frames = int(max_frames)
         self.cap = ((self.max_frames * h * w + 63) // 64) * 64
@@ -288,7 +299,7 @@ _reader_ws = {}
 
 
 def memory_reader_forward(m_key, m_val, q_key, q_val, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                          elem_format=ELEM_BF16, want_p=False):
+                          elem_format=ELEM_FP16, want_p=False):
     """Literal MemoryReader.forward (models/rmnet.py:147-165) -> mem_val [n,1024,h,w] (dense, region-agnostic);
     with want_p also the reference's second output p [n,T*h*w,h*w] -> (mem_val, p)."""
     for t, nm in ((m_key, "m_key"), (m_val, "m_val"), (q_key, "q_key"), (q_val, "q_val")):
@@ -328,13 +339,30 @@ def update_optical_flow_cuda(of, m1, m2):
     return out
 
 
-_flow_scratch = {}
+_flow_tls = __import__("threading").local()
 
 
-def update_optical_flow(of, m1, m2):
+def _cuda_usable_here():
+    """True when this process may launch on a CUDA device right now: a device exists, torch's CUDA context is already
+    initialised in THIS process (never initialise one just for a 6 MB elementwise op) and we are not a forked child of a
+    process that had initialised CUDA (a DataLoader worker: utils/data_transforms.py:293-302 runs there)."""
+    if not torch.cuda.is_available() or not torch.cuda.is_initialized():
+        return False
+    bad_fork = getattr(torch.cuda, "_is_in_bad_fork", None)
+    return not (bad_fork() if callable(bad_fork) else False)
+
+
+def update_optical_flow(of, m1, m2, device=None):
     """flow_affine_transformation.update_optical_flow(of, M1, M2) (flow_affine_transformation.cpp:39-85):
-    NumPy in, NumPy out; the arithmetic runs on the GPU (host buffers are staged through a device scratch).
-    Unlike the reference (no validation, .cpp:45-55) dtype / shape / contiguity are checked and converted."""
+    NumPy in, NumPy out, bit-exact with the reference extension either way it runs:
+
+      * on the GPU (host buffers staged through a per-thread device scratch) when this process already has a usable CUDA
+        context, or when device="cuda" is forced;
+      * by the library's plain-C entry point rmnet_update_optical_flow_cpu otherwise -- in particular inside forked
+        DataLoader workers, which is where the reference calls this op -- or when device="cpu" is forced.
+
+    Unlike the reference (no validation, .cpp:45-55) dtype / shape / contiguity are checked and converted (the
+    reference reads a float64 zeros array as float32 when a flow file is missing, utils/data_loaders.py:54-55)."""
     import numpy as np
     of = np.ascontiguousarray(of, dtype=np.float32)
     if of.ndim != 3 or of.shape[2] != 2:
@@ -343,16 +371,22 @@ def update_optical_flow(of, m1, m2):
     a2 = np.ascontiguousarray(np.asarray(m2, dtype=np.float32).reshape(-1)[:6])
     if a1.size != 6 or a2.size != 6:
         raise ValueError("affine matrices must be 2x3")
-    if not torch.cuda.is_available():
-        raise RuntimeError("rmnet_b200.update_optical_flow needs a CUDA device (no CPU fallback)")
     H, W = of.shape[:2]
+    out = np.empty_like(of)
+    use_cuda = _cuda_usable_here() if device is None else (str(device) != "cpu")
+    if not use_cuda:
+        check(lib().rmnet_update_optical_flow_cpu(of.ctypes.data, a1.ctypes.data, a2.ctypes.data, H, W, out.ctypes.data),
+              "update_optical_flow_cpu")
+        return out
+    if not torch.cuda.is_available():
+        raise RuntimeError("rmnet_b200.update_optical_flow(device='cuda') needs a CUDA device")
     dev = torch.device("cuda", torch.cuda.current_device())
     need = 2 * of.nbytes
-    sc = _flow_scratch.get(dev.index)
+    cache = _flow_tls.__dict__.setdefault("scratch", {})      # per thread: concurrent callers never share a staging buffer
+    sc = cache.get(dev.index)
     if sc is None or sc.numel() < need:
         sc = torch.empty(need, dtype=torch.uint8, device=dev)
-        _flow_scratch[dev.index] = sc
-    out = np.empty_like(of)
+        cache[dev.index] = sc
     check(lib().rmnet_update_optical_flow_host(of.ctypes.data, a1.ctypes.data, a2.ctypes.data, H, W, out.ctypes.data,
                                                sc.data_ptr(), sc.numel(), _stream(dev)), "update_optical_flow_host")
     return out

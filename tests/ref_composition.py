@@ -40,8 +40,9 @@ def torch_warp(img0, flow):
 class ReferenceClip:
     """Memory bank + per-frame step exactly as RMNet.forward / memorize / segment compose them (batch 1)."""
 
-    def __init__(self, gen, n, K, H, W):
+    def __init__(self, gen, n, K, H, W, per_object_reader=False):
         self.gen, self.n, self.K, self.H, self.W = gen, n, K, H, W
+        self.per_object_reader = per_object_reader   # run :155-160 one object at a time (p is 2 GB per object at 720p / T=40)
         self.h, self.w = (H + 15) // 16, (W + 15) // 16
         self.keys = self.vals = None
 
@@ -76,9 +77,18 @@ class ReferenceClip:
         v4e = cur["qv"][None].expand(n, -1, -1, -1) * a16                            # :333, :358
         m_key, m_val = this_keys[0, 1:n + 1].contiguous(), this_vals[0, 1:n + 1].contiguous()    # :348-349
         M, N = m_key.shape[2] * h * w, h * w
-        mi = torch.transpose(m_key.view(n, 128, M), 1, 2)                            # :151-152
-        p = torch.softmax(torch.bmm(mi, k4e.reshape(n, 128, N)) / math.sqrt(128), dim=1)   # :155-157
-        mem = torch.bmm(m_val.view(n, 512, M), p).view(n, 512, h, w)                 # :158-161
+        if self.per_object_reader:
+            mems = []
+            for o in range(n):
+                mi = torch.transpose(m_key[o:o + 1].view(1, 128, M), 1, 2)
+                p = torch.softmax(torch.bmm(mi, k4e[o:o + 1].reshape(1, 128, N)) / math.sqrt(128), dim=1)
+                mems.append(torch.bmm(m_val[o:o + 1].view(1, 512, M), p).view(1, 512, h, w))
+                del p
+            mem = torch.cat(mems, dim=0)
+        else:
+            mi = torch.transpose(m_key.view(n, 128, M), 1, 2)                        # :151-152
+            p = torch.softmax(torch.bmm(mi, k4e.reshape(n, 128, N)) / math.sqrt(128), dim=1)   # :155-157
+            mem = torch.bmm(m_val.view(n, 512, M), p).view(n, 512, h, w)             # :158-161
         return torch.cat([mem, v4e], dim=1), prev_bb, cur_bb                         # :163
 
 

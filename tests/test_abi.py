@@ -117,3 +117,76 @@ def test_frame_loop_host_logic_matches_the_reference_rules():
     m = channel_modes(K, n_max, existing, [0, 1, 3])          # object 3 is first annotated in this frame
     assert m == [CH_KEEP, CH_KEEP, CH_ABSENT, CH_NEW] + [CH_KEEP] * 7 and existing == [0, 1, 3]
     assert channel_modes(K, n_max, existing, [0, 1, 3]) == [CH_KEEP, CH_KEEP, CH_ABSENT, CH_KEEP] + [CH_KEEP] * 7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# update_optical_flow without a GPU: the library's plain-C entry point (the one a forked DataLoader worker gets)
+# ---------------------------------------------------------------------------------------------------------------
+def _flow_case(seed, H, W, half):
+    import synth
+    rng = np.random.default_rng(seed)
+    of = np.ascontiguousarray(np.moveaxis(synth.flow_field(rng, H, W, 4.0, half_pixel=half), 0, -1))
+    m1, m2 = synth.affine_pair(rng)
+    return of, m1, m2
+
+
+def test_update_optical_flow_cpu_entry_point_bit_exact_vs_golden_oracle_and_reference_extension(golden_dir):
+    """rmnet_update_optical_flow_cpu (flow_affine_transformation.cpp:63-83 in plain C, -ffp-contract=off) against the
+    golden vectors the unmodified reference extension produced, the C oracle, and the reference extension live."""
+    import glob
+    import sys
+    import synth
+    g = np.load(os.path.join(golden_dir, "flow_affine.npz"))
+    for i in range(int(g["n_cases"])):
+        seed, H, W = (int(g[f"c{i}_{k}"]) for k in ("seed", "H", "W"))
+        rng = np.random.default_rng(seed)
+        of = np.ascontiguousarray(np.moveaxis(synth.flow_field(rng, H, W, float(g[f"c{i}_sigma"])), 0, -1))
+        m1, m2 = synth.affine_pair(rng)
+        np.testing.assert_array_equal(ops.update_optical_flow(of, m1, m2, device="cpu"), g[f"c{i}_out"])
+    so = glob.glob(os.path.join(ROOT, "oracle", "_ref", "flow_affine_transformation*.so"))
+    ref = None
+    if so:
+        sys.path.insert(0, os.path.dirname(so[0]))
+        sys.modules.pop("flow_affine_transformation", None)
+        import flow_affine_transformation as ref
+    for s in range(8):
+        of, m1, m2 = _flow_case(300 + s, 37 + 31 * s, 50 + 17 * s, s % 2 == 0)
+        if s == 0:   # exact .5 ties for round-half-away
+            m1, m2 = np.array([[1, 0, 0.5], [0, 1, -0.5]], np.float32), np.array([[1, 0, 0], [0, 1, 0]], np.float32)
+        out = ops.update_optical_flow(of, m1, m2, device="cpu")
+        np.testing.assert_array_equal(out, oracle.update_optical_flow(of, m1, m2))
+        if ref is not None:
+            np.testing.assert_array_equal(out, ref.update_optical_flow(of, m1, m2))
+    # the reference's float64-zeros hazard (utils/data_loaders.py:54-55): converted, not reinterpreted
+    z = ops.update_optical_flow(np.zeros((8, 9, 2)), np.eye(2, 3), np.eye(2, 3), device="cpu")
+    assert z.dtype == np.float32 and not z.any()
+
+
+class _FlowDataset:
+    """A dataset whose __getitem__ calls the drop-in exactly where the reference does (RandomAffine.__call__,
+    utils/data_transforms.py:293-302): inside a DataLoader worker process."""
+
+    def __len__(self):
+        return 4
+
+    def __getitem__(self, i):
+        import flow_affine_transformation            # the drop-in module of that name (rmnet_b200/dropin on sys.path)
+        of, m1, m2 = _flow_case(900 + i, 64, 80, False)
+        return flow_affine_transformation.update_optical_flow(of, m1, m2)
+
+
+def test_update_optical_flow_dropin_runs_inside_forked_dataloader_workers():
+    import sys
+    import torch
+    dropin = os.path.join(ROOT, "rmnet_b200", "dropin")
+    sys.path.insert(0, dropin)
+    sys.modules.pop("flow_affine_transformation", None)
+    try:
+        loader = torch.utils.data.DataLoader(_FlowDataset(), batch_size=1, num_workers=2, multiprocessing_context="fork")
+        outs = [b[0].numpy() for b in loader]
+    finally:
+        sys.path.remove(dropin)
+        sys.modules.pop("flow_affine_transformation", None)
+    for i, out in enumerate(outs):
+        of, m1, m2 = _flow_case(900 + i, 64, 80, False)
+        np.testing.assert_array_equal(out, oracle.update_optical_flow(of, m1, m2))

@@ -16,6 +16,12 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import bench
     clips = bench.shard_clips(7, rank, world)
+    mine = bench.shard_longest_first([60 * 5] * 4, world)[rank]
+    labels = torch.full((len(mine), 3, 4, 5), rank + 1, dtype=torch.uint8)
+    maps = bench.gather_label_maps(labels, rank, world)
+    assert (maps is None) == (rank != 0)
+    if rank == 0:
+        assert [int(m.unique()) for m in maps] == [1, 2] and all(m.shape == (2, 3, 4, 5) and m.dtype == torch.uint8 for m in maps)
     dev_ms, e2e_s, sums = bench.reduce_over_ranks(10.0 + rank, 2.0 - rank, 100.0 * (rank + 1), torch.device("cpu"), rank, world)
     q.put((rank, clips, dev_ms, e2e_s, sums))
     dist.barrier()
@@ -43,3 +49,16 @@ def test_single_rank_is_a_no_op():
     import bench
     assert bench.shard_clips(3, 0, 1) == [0, 1, 2]
     assert bench.reduce_over_ranks(1.0, 2.0, 3.0, torch.device("cpu"), 0, 1) == (1.0, 2.0, [3.0])
+
+
+def test_longest_first_sharding_balances_and_covers_every_clip():
+    import bench
+    costs = [60 * n for n in (1, 2, 3, 4, 5)] * 3 + [104 * 5]
+    for world in (1, 2, 4, 8):
+        shards = bench.shard_longest_first(costs, world)
+        assert sorted(i for s in shards for i in s) == list(range(len(costs)))
+        loads = [sum(costs[i] for i in s) for s in shards]
+        assert max(loads) - min(loads) <= max(costs)                 # LPT bound
+    assert bench.shard_longest_first(costs, 2)[0][0] == len(costs) - 1   # the longest clip goes first, to rank 0
+    eq = bench.shard_longest_first([300] * 16, 8)
+    assert all(len(s) == 2 for s in eq)                              # equal clips -> equal shards (the gather needs that)
