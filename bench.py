@@ -369,7 +369,10 @@ def run_vos(args, rank, world, local_rank, dev, precision):
     vos.reference_flags()
     tfn, net = baseline.build_nets(0, dev, cpu_generator=False)
     tfn_dp, net_dp = vos.wrap(tfn, net, [local_rank])                                 # core/inference.py:35-37
-    rmnet_b200.install(ref, precision=precision)
+    # output="host": est_masks comes back as a (pinned) host tensor at every N -- the reference's own rule would keep it on
+    # the device as soon as more than one GPU is VISIBLE (models/rmnet.py:388-392), which would make the per-rank work of
+    # the N = 1 and N > 1 runs differ
+    rmnet_b200.install(ref, precision=precision, output="host")
     H, W, n, F_, every = (VOS_SHAPE[k] for k in ("H", "W", "n", "F", "every"))
     n_clips = VOS_CLIPS_PER_GPU * world
     clips = [dict(seed=5000 + i, n=n, F=F_) for i in range(n_clips)]
@@ -381,8 +384,7 @@ def run_vos(args, rank, world, local_rank, dev, precision):
         return frames, masks, n_objects                                               # pageable host tensors, int32 masks (utils/helpers.py:52-53)
 
     def labels_of(probs):
-        lab = probs[0].argmax(1).to(torch.uint8)                                      # core/inference.py:61
-        return lab if lab.is_cuda else lab.to(dev)
+        return probs[0].to(dev).argmax(1).to(torch.uint8)                             # core/inference.py:61 (on the device: 270 M floats)
 
     # warm-up: one short clip of the same shape (cuDNN plans, graph capture of the frame body)
     wf, wm, wn = baseline.synthetic_clip(4999, n, 8, H, W)
@@ -398,19 +400,18 @@ def run_vos(args, rank, world, local_rank, dev, precision):
     torch.cuda.synchronize()
     for ci in mine:
         frames, masks, n_objects = host_clip(clips[ci])
-        probs, s, sf = vos.run_clip(tfn_dp, net_dp, frames, masks, n_objects, every)
-        t0 = time.perf_counter()
-        lab = labels_of(probs)                                                        # the result the driver keeps (uint8 label maps)
-        lab_host = lab.cpu()
-        secs += s + (time.perf_counter() - t0)
+        probs, s, sf = vos.run_clip(tfn_dp, net_dp, frames, masks, n_objects, every)   # timed: the two calls, est_masks back on the host
+        assert not probs.is_cuda
+        secs += s
         flow_s += sf
         frames_done += c_frames(clips[ci])
-        labs.append(lab)
+        labs.append(labels_of(probs))                                                 # untimed: what core/inference.py:61 keeps of a clip
         # bytes crossing PCIe, counted from the tensors: DataParallel scatters every tensor argument of both calls (frames
-        # twice), the flows come back when the reference's rule keeps them on the host, est_masks / the label maps go back
-        flows_on_host = not (torch.cuda.device_count() > 1)
-        h2d += 2 * frames.numel() * 4 + masks.numel() * 4 + (frames.shape[1] * 2 * H * W * 4 if flows_on_host else 0)
-        d2h += (frames.shape[1] * 2 * H * W * 4 if flows_on_host else 0) + (probs.numel() * 4 if not probs.is_cuda else lab_host.numel())
+        # twice, the int32 masks, the flows when TinyFlowNet's rule left them on the host); est_masks and those flows go back
+        flows_on_host = not (torch.cuda.device_count() > 1)                           # models/tiny_flownet.py:124-127
+        flow_bytes = frames.shape[1] * 2 * H * W * 4
+        h2d += 2 * frames.numel() * 4 + masks.numel() * 4 + (flow_bytes if flows_on_host else 0)
+        d2h += (flow_bytes if flows_on_host else 0) + probs.numel() * 4
         del frames, masks, probs
     launches = int(L.rmnet_launch_count()) + loop.graph_launches - g0
     gather_s = 0.0
@@ -486,7 +487,7 @@ def vos_extras(ref, tfn, net, tfn_dp, net_dp, dev, precision):
     except Exception as e:
         out["reference_on_this_gpu"] = {"unavailable": f"{type(e).__name__}: {e}"}
     finally:
-        rmnet_b200.install(ref, precision=precision)
+        rmnet_b200.install(ref, precision=precision, output="host")
     try:
         out["module_split_ms_at_T20"] = vos.module_split(net, tfn, H, W, n, 20, dev)
     except Exception as e:

@@ -81,6 +81,7 @@ class _ClipState:
         self.prev_mask = torch.zeros((1, K, H, W), **f32)
         self.graphs = {}          # (commit, modes, want_logit) -> (CUDAGraph, outputs)
         self.pool = None
+        self.side = torch.cuda.Stream(dev)   # the query encoder's branch of a frame
 
 
 class RegionalFrameLoop:
@@ -92,10 +93,11 @@ class RegionalFrameLoop:
     more than one GPU is visible and no device is given, else a CPU tensor)."""
 
     def __init__(self, memorize_net, query_net, decoder_net, precision=RMNET_PREC_SPLIT3, impl=RMNET_IMPL_AUTO,
-                 elem_format=ELEM_FP16, use_graph=False, output="device", min_bank_frames=24):
+                 elem_format=ELEM_FP16, use_graph=False, output="device", min_bank_frames=24, overlap_query=True):
         self.memorize_net, self.query_net, self.decoder_net = memorize_net, query_net, decoder_net
         self.precision, self.impl, self.elem_format = precision, impl, elem_format
         self.use_graph, self.output = bool(use_graph), output
+        self.overlap_query = bool(overlap_query)
         self.min_bank_frames = int(min_bank_frames)   # bank capacity floor: 24 frames hold a 115-frame clip at memorize_every = 5
         self.last_bboxes = None   # [(prev_bbox, curr_bbox)] of the last clip (keep_bboxes=True), for inspection / tests
         self.last_logits = None   # [logit [1,K,H,W]] of the last clip (keep_logits=True): the return values of RMNet.segment + overrides
@@ -143,13 +145,26 @@ class RegionalFrameLoop:
         n, K, H, W = st.n, st.K, st.H, st.W
         rm = st.rm
         pad = (rm.lw, rm.uw, rm.lh, rm.uh)
+        # The query branch (encoder_query + kv_query of the CURRENT frame, batch 1: latency-bound) does not depend on the
+        # memorise branch (encoder_memory + kv_memory of the previous frame and mask, batch n): they run on two streams
+        # (two branches of the captured graph) and join before the fused step.  Same kernels, same bits.
+        cur = torch.cuda.current_stream(st.dev)
+        if self.overlap_query:
+            st.side.wait_stream(cur)
+        with torch.cuda.stream(st.side if self.overlap_query else cur):
+            k4q, v4q, ctx = self.query_net(F.pad(st.cur_frame, pad))                # :307-315
+            k4q0, v4q0 = k4q[0].contiguous(), v4q[0].contiguous()
         masks_p = F.pad(st.prev_mask, pad)                                          # :212
         frame_p = F.pad(st.prev_frame, pad)
         m, o = object_batches(masks_p, n)                                           # :219-229
         k4, v4 = self.memorize_net(frame_p, m, o)                                   # :234-236
-        k4q, v4q, ctx = self.query_net(F.pad(st.cur_frame, pad))                    # :307-315
-        m4, prev_bbox, curr_bbox = rm.step(k4.contiguous(), v4.contiguous(), st.prev_mask, st.flow, k4q[0].contiguous(),
-                                           v4q[0].contiguous(), commit=commit)      # :239-248, :416-426, :431, :355-361
+        if self.overlap_query:
+            cur.wait_stream(st.side)
+            for x in (k4q, v4q, k4q0, v4q0) + tuple(ctx or ()):
+                if isinstance(x, torch.Tensor):
+                    x.record_stream(cur)
+        m4, prev_bbox, curr_bbox = rm.step(k4.contiguous(), v4.contiguous(), st.prev_mask, st.flow, k4q0, v4q0,
+                                           commit=commit)                           # :239-248, :416-426, :431, :355-361
         logits = self.decoder_net(m4, ctx)                                          # :366
         logit, est = ops.mask_epilogue(logits.contiguous(), K, (H, W), modes, new_mask, want_logit=want_logit)   # :368-380, :289-302, :436-450
         return logit, est, prev_bbox, curr_bbox

@@ -98,13 +98,15 @@ def test_step_matches_the_reference_composition_at_headline_size(name, H, W, n, 
     torch.cuda.empty_cache()
 
 
-@pytest.mark.parametrize("scale,tol", [(0.35, 2e-5), (1.0, 2e-4), (2.0, 3e-4), (3.5, 6e-4), (6.0, 1e-3)],
-                         ids=["score~6", "score~50", "score~200", "score~600", "score~1800"])
+@pytest.mark.parametrize("scale,tol", [(0.35, 2e-6), (1.0, 5e-6), (2.0, 6e-5), (3.5, 1.2e-4), (6.0, 3e-4), (10.0, 1e-3)],
+                         ids=["score~1", "score~5", "score~22", "score~66", "score~194", "score~540"])
 def test_dense_reader_vs_fp64_oracle_across_score_magnitudes(scale, tol):
-    """Strict (bf16 hi/lo x3) reader vs the fp64 oracle when the scaled scores k.q/sqrt(128) grow from O(10) to O(1000):
-    the operands carry 16 mantissa bits, so the score error grows with |score|.  `tol` is the max-abs bound on
-    mem_val each regime is held to (values are N(0,1)); north_star's bound is 1e-3 on the LOGIT map, which the real-decoder
-    test (tests/test_gpu_rmnet.py) checks at |score| ~ 640.  The fp32 reference reader's own distance to fp64 is printed."""
+    """Strict (fp16 hi/lo planes x3) reader vs the fp64 oracle when the scaled scores k.q/sqrt(128) grow from O(1) to
+    O(500): the operands carry 22 mantissa bits, so the score error grows with |score|.  `tol` is the max-abs
+    bound on mem_val each regime is held to (values are N(0,1)) -- about 2.5x what was measured on the B200 (2.3e-7,
+    8.1e-7, 1.8e-5, 3.6e-5, 1.1e-4 for scales 0.35 .. 6), which is also what the reference's own fp32 reader is away from
+    fp64 (printed).  north_star's bound is 1e-3 on the LOGIT map; the real-decoder test (tests/test_gpu_rmnet.py) checks
+    that at |score| ~ 640."""
     n, T, h, w = 2, 4, 30, 54
     ins = synth.memory_read_inputs(4242, n, T, h, w, scale)
     ref64, _ = oracle.memory_read(*ins, dtype=np.float64)
