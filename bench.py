@@ -419,6 +419,7 @@ def run_vos(args, rank, world, local_rank, dev, precision):
     if world > 1:
         import torch.distributed as dist
         stack = torch.stack(labs)                                                     # [clips, F, H, W] uint8
+        gather_label_maps(stack[:1, :1].contiguous(), rank, world)                    # untimed: NCCL sets its channels up on first use
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         outs = gather_label_maps(stack, rank, world)                                  # the one collective of the job

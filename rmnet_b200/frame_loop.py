@@ -29,6 +29,11 @@ from ._lib import CH_ABSENT, CH_KEEP, CH_NEW, ELEM_FP16, RMNET_IMPL_AUTO, RMNET_
 from .modules import RegionalMemory
 
 
+# kernels of this library launched through CUDA-graph replays by every loop of this process (rmnet_launch_count() counts
+# only eager launches); [0] so that importers see updates
+graph_launch_total = [0]
+
+
 def object_batches(masks_p, n):
     """The per-object mask batches of RMNet.memorize (models/rmnet.py:219-229): m = the object's soft mask, o = the other
     objects' masks summed (before + after, in the reference's order) and clamped.  masks_p [1,K,Hp,Wp] -> ([n,Hp,Wp], [n,Hp,Wp])"""
@@ -196,6 +201,7 @@ class RegionalFrameLoop:
             raise RuntimeError(f"memory bank full: {rm.bank.frames_committed} committed frames, capacity {rm.bank.max_frames}")
         g.replay()
         self.graph_launches += captured
+        graph_launch_total[0] += captured
         if commit:
             rm.bank.frames_committed += 1
             rm.bank.has_temp = False

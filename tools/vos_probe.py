@@ -55,6 +55,29 @@ leg("reference", ref_leg)
 leg("ours_eager", our_leg(False))
 leg("ours_graph", our_leg(True))
 leg("ours_graph_device", our_leg(True, "device"))
+def cl_leg(bench_flag):
+    def f():
+        torch.backends.cudnn.benchmark = bench_flag
+        net.to(memory_format=torch.channels_last); tfn.to(memory_format=torch.channels_last)
+        try:
+            our_leg(True, "host")()
+            res[f"ours_channels_last_benchmark{int(bench_flag)}"] = res.pop("ours_graph1_host")
+        finally:
+            net.to(memory_format=torch.contiguous_format); tfn.to(memory_format=torch.contiguous_format)
+            torch.backends.cudnn.benchmark = False
+    return f
+
+def bench_only_leg():
+    torch.backends.cudnn.benchmark = True
+    try:
+        our_leg(True, "host")()
+        res["ours_nchw_benchmark1"] = res.pop("ours_graph1_host")
+    finally:
+        torch.backends.cudnn.benchmark = False
+
+leg("nchw_benchmark", bench_only_leg)
+leg("channels_last", cl_leg(False))
+leg("channels_last_benchmark", cl_leg(True))
 leg("split", lambda: res.__setitem__("module_split_ms", vos.module_split(net, tfn, H, W, n, 5, dev)))
 res.pop("_ref_lab", None)
 print(json.dumps(res, indent=1))
