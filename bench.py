@@ -616,6 +616,7 @@ def run_gpu(args, wl, rank, world, local_rank):
         evs.append((a, b))
     barrier()
     launches = int(L.rmnet_launch_count())
+    checksum = float(m4.double().sum().item())     # of the last timed step's mem_val: rank 0's equals the N = 1 run's (same pool seed)
     step_ms = [a.elapsed_time(b) for a, b in evs]
     dev_ms = float(np.sum(step_ms))
     if os.environ.get("RMNET_BENCH_DEBUG"):
@@ -786,7 +787,6 @@ def run_gpu(args, wl, rank, world, local_rank):
             vos_info = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-1200:]}
 
     # ---- max over ranks (device time, op-level e2e time, VOS time); sum of the frames segmented; checksums gathered
-    checksum = float(m4.double().sum().item())
     dev_ms, e2e_s, sums = reduce_over_ranks(dev_ms, e2e_s, checksum, dev, rank, world)
     vos_max_s, vos_total_frames = vos_s, vos_frames
     if world > 1 and vos_s is not None:
