@@ -32,11 +32,9 @@ struct PackSmem {
 // 64 compact cells x 128 key channels: gather from the channels-first frame -> 16-bit hi/lo split -> transpose through
 // smem -> 256 B position-major rows.  Rows [cnt, rows) are written as zeros.
 // INTERLEAVED = false: plain rows (the TMA / UMMA operand layout of the bank).
-// INTERLEAVED = true : query planes for the read kernel.  The HI plane is read by threads (thread r of a warp owns row r
-//   of a 32-row group and loads it 16 B at a time): chunk j of the 32 rows is stored contiguously ([group][16 chunks]
-//   [32 rows][8 ch]) so that every such warp load is one coalesced 512 B access.  The LO plane is fetched by TMA into
-//   shared memory (A operand of the Ql.Kh product) and keeps plain 256 B rows.  dst_* point at the first row of a
-//   32-aligned group.
+// INTERLEAVED = true : query planes for the read kernel, whose thread r of a warp owns row r of a 32-row group and loads
+//   it 16 B at a time: chunk j of the 32 rows is stored contiguously ([group][16 chunks][32 rows][8 ch]) so that
+//   every such warp load is one coalesced 512 B access.  dst_* point at the first row of a 32-aligned group.
 template <int FMT, bool INTERLEAVED>
 __device__ __forceinline__ bool pack_key_rows(PackSmem &sm, const float *__restrict__ src, long long ch_stride, const int4 rect,
                                               int w, int i0, int cnt, int rows, uint16_t *__restrict__ dst_hi,
@@ -68,7 +66,7 @@ __device__ __forceinline__ bool pack_key_rows(PackSmem &sm, const float *__restr
         const uint2 l0 = *reinterpret_cast<const uint2 *>(&sm.lo[row][j * 8]), l1 = *reinterpret_cast<const uint2 *>(&sm.lo[row][j * 8 + 4]);
         const size_t g = ((size_t)(g32 * 16 + j) * 32 + lane) * 8;  // ushorts
         *reinterpret_cast<uint4 *>(dst_hi + g) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-        *reinterpret_cast<uint4 *>(dst_lo + (size_t)row * RMNET_CK + j * 8) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+        *reinterpret_cast<uint4 *>(dst_lo + g) = make_uint4(l0.x, l0.y, l1.x, l1.y);
       }
     }
   } else {

@@ -3,22 +3,17 @@
 // One CTA = (128 in-region queries) x (one object) x (one half of the 512 value channels) x (one KV split).
 // It streams the object's region-compacted bank in tiles of 64 memory cells and keeps everything on chip:
 //
-//   warp 0 : TMA producer for key tiles   (cp.async.bulk.tensor, SWIZZLE_128B, 2-stage mbarrier ring)
+//   warp 0 : TMA producer for key tiles   (cp.async.bulk.tensor, SWIZZLE_128B, 3-stage mbarrier ring)
 //   warp 2 : TMA producer for value tiles (2-stage ring)
-//   warp 3 : builds the schedule, then TMA-loads the lo plane of each piece's query keys into shared memory
 //   warp 1 : MMA issuer -- one elected thread issues tcgen05.mma (kind::f16, fp32 accumulate in TMEM):
-//              S[128 q x 64 m]   = Q . K^T      A = Q hi from TMEM / Q lo from smem, B = K tile (smem, K-major)
+//              S[128 q x 64 m]   = Q . K^T      A = Q  from TMEM, B = K tile (smem, K-major)
 //              O[128 q x 256 cv] += P . V^T     A = P  from TMEM, B = V tile (smem, K-major)
-//            in strict mode every product is the 3-term hi/lo split  Ah.Bh + Ah.Bl + Al.Bh  (SURVEY 7.3).
-//            The score MMAs of tile i+2 (N = 64: 48 cycles each issued back to back, 32 nominal) are INTERLEAVED with
-//            the P.V MMAs of tile i (N = 256, 128 cycles): (QK, QK, PV) x 12 runs at the 2 304-cycle floor of the 36 MMAs
-//            (tools/probes/mma_chain_probe.cu), which takes THREE S/P buffers -- tile i+2 is written while tile i is read
-//            and tile i+1 is in the softmax warpgroup.
+//            in strict mode every product is the 3-term hi/lo split  Ah.Bh + Ah.Bl + Al.Bh  
 //   warps 4-7 : softmax warpgroup, one thread per query row (TMEM lane): tcgen05.ld S -> scale -> lazy online
 //            max -> exp2 -> hi/lo split of P -> tcgen05.st P over the S columns; rescales O in TMEM only when
 //            the running max grows by more than 2^8; epilogue tcgen05.ld O -> coalesced partial stores.
 //
-// TMEM (512 columns x 128 lanes): O [0,256) | S/P buffers 0..2 [256,448) | Q hi [448,512); the Q lo plane lives in smem (32 KB)
+// TMEM (512 columns x 128 lanes): O [0,256) | S/P buffer 0 [256,320) | S/P buffer 1 [320,384) | Q hi [384,448) | Q lo [448,512)
 // Masked (never stored) memory cells and out-of-region queries are handled analytically by merge.cu.
 //
 // Reference math: models/rmnet.py:147-165 (MemoryReader.forward) with the regional masks of :245-248 / :355-358.
@@ -32,8 +27,7 @@ namespace {
 constexpr int QT = 128;   // queries per CTA  (UMMA M)
 constexpr int MT = 64;    // memory cells per KV tile
 constexpr int CVH = 256;  // value channels per CTA (UMMA N of the P.V product)
-constexpr int KST = 2;    // key-tile ring depth
-constexpr int NSB = 3;    // S/P buffers in TMEM
+constexpr int KST = 3;    // key-tile ring depth
 constexpr int VST = 2;    // value-tile ring depth
 constexpr int kThreads = 256;
 constexpr float kTau = 8.0f;  // lazy-rescale threshold (log2 units): P stays <= 2^8
@@ -42,12 +36,11 @@ constexpr uint32_t K_PLANE_BYTES = MT * RMNET_CK * 2;       // 16 KB: [64 cells]
 constexpr uint32_t K_STAGE_BYTES = 2 * K_PLANE_BYTES;       // hi + lo
 constexpr uint32_t V_PLANE_BYTES = CVH * MT * 2;            // 32 KB: [256 ch][64 cells]
 constexpr uint32_t V_STAGE_BYTES = 2 * V_PLANE_BYTES;
-constexpr uint32_t QL_BYTES = QT * RMNET_CK * 2;            // 32 KB: lo plane of the piece's 128 query keys, two SW128 blocks of 64 channels
-constexpr uint32_t SMEM_TILES = KST * K_STAGE_BYTES + VST * V_STAGE_BYTES + QL_BYTES;  // 224 KB
+constexpr uint32_t SMEM_TILES = KST * K_STAGE_BYTES + VST * V_STAGE_BYTES;  // 224 KB
 constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // TMEM column map
-constexpr uint32_t TM_O = 0, TM_S0 = 256, TM_Q_HI = 448;
+constexpr uint32_t TM_O = 0, TM_S0 = 256, TM_Q_HI = 384, TM_Q_LO = 448;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,13 +106,6 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem]^T
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,8 +159,7 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t &hi, ui
 
 struct Barriers {
   uint64_t k_full[KST], k_empty[KST], v_full[VST], v_empty[VST];
-  uint64_t s_full[NSB], p_full[NSB], pv_done[NSB], q_ready;
-  uint64_t ql_full, ql_free;  // lo plane of the piece's query keys in smem: loaded (TMA tx) / no longer read by any score MMA
+  uint64_t s_full[2], p_full[2], pv_done[2], q_ready;
   uint32_t tmem_base;
 };
 
@@ -210,8 +195,7 @@ template <int FMT, bool USE_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
-                        const __grid_constant__ CUtensorMap map_qlo,
-                        const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi,
+                        const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
                         const int *__restrict__ q_rects, int h, int w,
                         float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
                         int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg_arg, int dbg_flags_arg) {
@@ -229,7 +213,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   Barriers *bars = reinterpret_cast<Barriers *>(smem_al + SMEM_TILES);
-  const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES, ql_smem = v_smem + VST * V_STAGE_BYTES;
+  const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
   __shared__ SchedTable sched;
 
 #ifdef RMNET_DEV
@@ -249,17 +233,14 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   if (tstamp && threadIdx.x == 32) tstamp[10] = clock64();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
-    tma_prefetch_desc(&map_qlo);
     for (int i = 0; i < KST; ++i) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
     for (int i = 0; i < VST; ++i) { mbar_init(smem_u32(&bars->v_full[i]), 1); mbar_init(smem_u32(&bars->v_empty[i]), 1); }
-    for (int i = 0; i < NSB; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
       mbar_init(smem_u32(&bars->p_full[i]), 128);
       mbar_init(smem_u32(&bars->pv_done[i]), 1);
     }
     mbar_init(smem_u32(&bars->q_ready), 128);
-    mbar_init(smem_u32(&bars->ql_full), 1);
-    mbar_init(smem_u32(&bars->ql_free), 1);
     fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM: the smem footprint guarantees it)
@@ -334,98 +315,71 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         }
       }
     }
-  } else if (warp == 3) {
-    // ================= lo plane of each piece's query keys -> shared memory (A operand of the Ql.Kh product) =================
-    if (use_lo && lane == 0) {
-      if (early) pdl_wait();  // the planes are written by the pack kernel's query role
-      int np = 0;
-      while (iter.next(pc)) {
-        if (np > 0) mbar_wait(smem_u32(&bars->ql_free), (np - 1) & 1);  // every score MMA of the previous piece has retired
-        const uint32_t full = smem_u32(&bars->ql_full);
-        mbar_expect_tx(full, QL_BYTES);
-        tma_load_3d(ql_smem, &map_qlo, full, 0, pc.qtile * QT, pc.o);
-        tma_load_3d(ql_smem + QL_BYTES / 2, &map_qlo, full, 64, pc.qtile * QT, pc.o);
-        ++np;
-      }
-    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     const uint32_t idesc_qk = umma_idesc(fmt, MT), idesc_pv = umma_idesc(fmt, CVH);
-    // One k-step (16 channels) of the score product of the tile in key stage `s` into S/P buffer `b`: up to 3 MMAs.
-    auto qk_step = [&](int s, int b, int kk) {
-      // 16 channels = 32 B inside the 128 B swizzle row; channels 64..127 live in the second block of the plane
-      const uint32_t off = (kk >> 2) * (K_PLANE_BYTES / 2) + (kk & 3) * 32;
-      const uint32_t kb = k_smem + s * K_STAGE_BYTES;
-      const uint32_t d = tmem + TM_S0 + b * MT;
-      const uint64_t bh = umma_desc_sw128(kb + off);
-      umma_ts(d, tmem + TM_Q_HI + kk * 8, bh, idesc_qk, kk > 0 ? 1u : 0u);
-      if (use_lo) {
-        umma_ts(d, tmem + TM_Q_HI + kk * 8, umma_desc_sw128(kb + K_PLANE_BYTES + off), idesc_qk, 1u);
-        umma_ss(d, umma_desc_sw128(ql_smem + (kk >> 2) * (QL_BYTES / 2) + (kk & 3) * 32), bh, idesc_qk, 1u);
+    int gt = 0;       // tiles whose score MMA has been issued (global over pieces: S/P buffer + key ring position)
+    auto issue_qk = [&]() {
+      const int s = gt % KST, b = gt & 1;
+      mbar_wait(smem_u32(&bars->k_full[s]), (gt / KST) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t kb = k_smem + s * K_STAGE_BYTES;
+        const uint32_t d = tmem + TM_S0 + b * MT;
+#pragma unroll
+        for (int kk = 0; kk < RMNET_CK / 16; ++kk) {
+          // 16 channels = 32 B inside the 128 B swizzle row; channels 64..127 live in the second 8 KB block
+          const uint32_t off = (kk >> 2) * (K_PLANE_BYTES / 2) + (kk & 3) * 32;
+          const uint64_t bh = umma_desc_sw128(kb + off);
+          umma_ts(d, tmem + TM_Q_HI + kk * 8, bh, idesc_qk, kk > 0 ? 1u : 0u);
+          if (use_lo) {
+            const uint64_t bl = umma_desc_sw128(kb + K_PLANE_BYTES + off);
+            umma_ts(d, tmem + TM_Q_HI + kk * 8, bl, idesc_qk, 1u);
+            umma_ts(d, tmem + TM_Q_LO + kk * 8, bh, idesc_qk, 1u);
+          }
+        }
+        umma_commit(smem_u32(&bars->k_empty[s]));  // key stage free once these MMAs retire
+        umma_commit(smem_u32(&bars->s_full[b]));   // scores ready for the softmax warpgroup
       }
+      __syncwarp();
+      ++gt;
     };
-    // One k-step (16 cells) of the P.V product of S/P buffer `b` with value stage `s`: up to 3 MMAs of N = 256.
-    auto pv_step = [&](int s, int b, int kk, bool first) {
-      const uint32_t vb = v_smem + s * V_STAGE_BYTES;
-      const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
-      const uint64_t bh = umma_desc_sw128(vb + kk * 32);
-      umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, first ? 0u : 1u);
-      if (use_lo) {
-        umma_ts(tmem + TM_O, p_hi + kk * 8, umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32), idesc_pv, 1u);
-        umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
-      }
-    };
-    int gt = 0;       // tiles whose score MMAs have been issued (global over pieces: S/P buffer + key ring position)
-    int pt = 0;       // tiles whose P.V MMAs have been issued (global)
+    int pt = 0;       // tiles whose P.V MMA has been issued (global)
     int n_piece = 0;
     while (iter.next(pc)) {
-      mbar_wait(smem_u32(&bars->q_ready), n_piece & 1);              // this piece's Q hi rows are in TMEM ...
-      if (use_lo) mbar_wait(smem_u32(&bars->ql_full), n_piece & 1);  // ... and its Q lo rows in shared memory
+      mbar_wait(smem_u32(&bars->q_ready), n_piece & 1);  // this piece's Q rows are in TMEM
       tc_fence_after();
       ++n_piece;
-      // software pipeline over the piece's tiles:  QK(0) QK(1) | PV(0)+QK(2) | PV(1)+QK(3) | ... | PV(n-2) | PV(n-1)
-      // In a steady-state step the 24 score MMAs of tile st and the 12 P.V MMAs of tile st-2 are issued INTERLEAVED
-      // (QK, QK, PV): they touch different S/P buffers (st % 3 is written, (st-2) % 3 is read) and different
-      // accumulators, and the short score MMAs then hide behind the long ones instead of paying their 48-cycle floor.
+      // software pipeline, one code site per product: QK(0) QK(1) | PV(0) QK(2) | PV(1) QK(3) | ... | PV(n-2) | PV(n-1)
+      // QK(s) overwrites the S/P buffer that PV(s-2) just consumed: the tensor pipe executes in issue order.
 #pragma unroll 1
       for (int st = 0; st < pc.n_it + 2; ++st) {
-        const bool do_pv = st >= 2, do_qk = st < pc.n_it;
-        const int ks = gt % KST, sb = gt % NSB;     // key stage / S buffer of the tile whose scores are computed
-        const int vs = pt % VST, pb = pt % NSB;     // value stage / P buffer of the tile that is accumulated
-        if (do_pv) {
-          mbar_wait(smem_u32(&bars->p_full[pb]), (pt / NSB) & 1);
-          mbar_wait(smem_u32(&bars->v_full[vs]), (pt / VST) & 1);
-        }
-        if (do_qk) mbar_wait(smem_u32(&bars->k_full[ks]), (gt / KST) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          if (do_pv && do_qk) {
+        if (st >= 2) {
+          const int it = st - 2;
+          const int s = pt % VST, b = pt & 1;
+          mbar_wait(smem_u32(&bars->p_full[b]), (pt >> 1) & 1);
+          mbar_wait(smem_u32(&bars->v_full[s]), (pt / VST) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t vb = v_smem + s * V_STAGE_BYTES;
+            const uint32_t p_hi = tmem + TM_S0 + b * MT, p_lo = p_hi + MT / 2;
 #pragma unroll
-            for (int kk = 0; kk < MT / 16; ++kk) {   // 4 x (2 score k-steps, 1 P.V k-step)
-              qk_step(ks, sb, 2 * kk);
-              qk_step(ks, sb, 2 * kk + 1);
-              pv_step(vs, pb, kk, st == 2 && kk == 0);
+            for (int kk = 0; kk < MT / 16; ++kk) {
+              const uint64_t bh = umma_desc_sw128(vb + kk * 32);
+              umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
+              if (use_lo) {
+                const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
+                umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
+                umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
+              }
             }
-          } else if (do_pv) {
-#pragma unroll
-            for (int kk = 0; kk < MT / 16; ++kk) pv_step(vs, pb, kk, st == 2 && kk == 0);
-          } else if (do_qk) {
-#pragma unroll
-            for (int kk = 0; kk < RMNET_CK / 16; ++kk) qk_step(ks, sb, kk);
+            umma_commit(smem_u32(&bars->v_empty[s]));
+            umma_commit(smem_u32(&bars->pv_done[b]));
           }
-          if (do_pv) {
-            umma_commit(smem_u32(&bars->v_empty[vs]));
-            umma_commit(smem_u32(&bars->pv_done[pb]));
-          }
-          if (do_qk) {
-            umma_commit(smem_u32(&bars->k_empty[ks]));  // key stage free once these MMAs retire
-            umma_commit(smem_u32(&bars->s_full[sb]));   // scores ready for the softmax warpgroup
-            if (use_lo && st == pc.n_it - 1) umma_commit(smem_u32(&bars->ql_free));  // last score MMA of the piece: Q lo may be replaced
-          }
+          __syncwarp();
+          ++pt;
         }
-        __syncwarp();
-        if (do_pv) ++pt;
-        if (do_qk) ++gt;
+        if (st < pc.n_it) issue_qk();
       }
     }
   } else if (warp >= 4) {
@@ -438,18 +392,24 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     bool first_piece = true;
     if (early) pdl_wait();  // the packed query keys (and, through the barriers, everything downstream) need the pack kernel
     pdl_trigger();          // after the wait: the merge kernel's pre-wait part relies on the bank being final
-    // this row's 128 query-key channels as packed 16-bit pairs (hi plane), written by the pack kernel's
+    // this row's 128 query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's
     // query role in the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that
     // each of the loads below is one coalesced 512 B access per warp
-    // (the lo plane goes to shared memory by TMA, warp 3)
-    uint32_t qh[RMNET_CK / 2];
+    uint32_t qh[RMNET_CK / 2], ql[USE_LO ? RMNET_CK / 2 : 1];
     auto fetch_q = [&](const Piece &p) {
       const size_t r = ((size_t)p.o * nq_pad + p.qtile * QT + (row & ~31)) * (RMNET_CK / 8) + (row & 31);  // uint4 units
-      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r;
+      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r, *pl = reinterpret_cast<const uint4 *>(qlo) + r;
 #pragma unroll
       for (int j = 0; j < RMNET_CK / 8; ++j) {
         const uint4 v = __ldg(ph + j * 32);
         qh[4 * j] = v.x; qh[4 * j + 1] = v.y; qh[4 * j + 2] = v.z; qh[4 * j + 3] = v.w;
+      }
+      if (USE_LO) {
+#pragma unroll
+        for (int j = 0; j < RMNET_CK / 8; ++j) {
+          const uint4 v = __ldg(pl + j * 32);
+          ql[4 * j] = v.x; ql[4 * j + 1] = v.y; ql[4 * j + 2] = v.z; ql[4 * j + 3] = v.w;
+        }
       }
     };
     // One code site per phase.  Order per piece k:  [Q(k) -> TMEM]  [drain O(k-1)]  [tiles of k]  -- so the tensor pipe
@@ -467,7 +427,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         fetch_q(nxt);
         if (tstamp && first_piece && row == 0) tstamp[13] = clock64();
 #pragma unroll
-        for (int c = 0; c < RMNET_CK / 2; c += 16) TMEM_ST16(t_base + TM_Q_HI + c, qh, c);
+        for (int c = 0; c < RMNET_CK / 2; c += 16) {
+          TMEM_ST16(t_base + TM_Q_HI + c, qh, c);
+          if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c, ql, c);
+        }
         if (tstamp && first_piece && row == 0) tstamp[14] = clock64();
         tc_wait_st();
         tc_fence_before();
@@ -477,7 +440,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       if (have_cur) {
         // ---- epilogue of the current piece: unnormalised numerators for merge.cu, partial slot pc.slot
         const int n = pc.qtile * QT + row;
-        mbar_wait(smem_u32(&bars->pv_done[(gt_done - 1) % NSB]), ((gt_done - 1) / NSB) & 1);
+        mbar_wait(smem_u32(&bars->pv_done[(gt_done - 1) & 1]), ((gt_done - 1) >> 1) & 1);
         tc_fence_after();
         if (tstamp && first_piece && row == 0) tstamp[5] = clock64();
         float *ob = opart + (((size_t)pc.slot * n_obj + pc.o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
@@ -512,9 +475,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
 
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int it = 0; it < pc.n_it; ++it, ++gt) {
-        const int b = gt % NSB;
+        const int b = gt & 1;
         const uint32_t s_addr = t_base + TM_S0 + b * MT;
-        mbar_wait(smem_u32(&bars->s_full[b]), (gt / NSB) & 1);
+        mbar_wait(smem_u32(&bars->s_full[b]), (gt >> 1) & 1);
         tc_fence_after();
         uint32_t sr[MT];
         TMEM_LD16(s_addr, sr, 0);
@@ -546,7 +509,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
           // lazy rescale of the O accumulator (rare after the first tiles): PV(it-1) must have retired, PV(it) cannot
           // start before this warp arrives on p_full below.
-          mbar_wait(smem_u32(&bars->pv_done[(gt - 1) % NSB]), ((gt - 1) / NSB) & 1);
+          mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = fmaxf(m_ref, mx);
           const float f = exp2f(m_ref - m_new);
@@ -685,23 +648,6 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
     mc = &c;
   }
   const CUtensorMap &mkh = mc->m[0], &mkl = mc->m[1], &mvh = mc->m[2], &mvl = mc->m[3];
-  // lo plane of the packed query keys, plain rows [n_obj][nq_pad][128]: box 64 ch x 128 rows (one piece's query tile)
-  struct QMapCache { const void *qlo; int nq_pad, n_obj; CUtensorMap m; };
-  static thread_local QMapCache qcache[4] = {};
-  static thread_local int qcache_next = 0;
-  const QMapCache *qc = nullptr;
-  for (int i = 0; i < 4; ++i)
-    if (qcache[i].qlo == W.qlo && qcache[i].nq_pad == W.nq_pad && qcache[i].n_obj == n_obj) qc = &qcache[i];
-  if (!qc) {
-    QMapCache &c = qcache[qcache_next];
-    qcache_next = (qcache_next + 1) & 3;
-    c.qlo = nullptr;
-    int rc;
-    if ((rc = make_map(&c.m, W.qlo, RMNET_CK, (uint64_t)W.nq_pad, (uint64_t)n_obj, RMNET_CK * 2, (uint64_t)W.nq_pad * RMNET_CK * 2, 64, QT))) return rc;
-    c.qlo = W.qlo; c.nq_pad = W.nq_pad; c.n_obj = n_obj;
-    qc = &c;
-  }
-  const CUtensorMap &mql = qc->m;
   const int n_sms = umma_grid_size();
   dim3 grid(n_sms);
   (void)n_splits;
@@ -716,8 +662,8 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
                                       (int)SMEM_BYTES));                                                                 \
       if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                                 \
     }                                                                                                                    \
-    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, mql, \
-                             bank.meta, W.qhi, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,                  \
+    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
+                             bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
                              temp_rects, bank.cap, g_dbg, g_dbg_flags));                                                 \
   } while (0)
   if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
