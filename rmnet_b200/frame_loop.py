@@ -103,6 +103,7 @@ class RegionalFrameLoop:
         self.precision, self.impl, self.elem_format = precision, impl, elem_format
         self.use_graph, self.output = bool(use_graph), output
         self.overlap_query = bool(overlap_query)
+        self.max_cached_states = 8                    # (object count, frame shape) combinations kept warm between clips
         self.min_bank_frames = int(min_bank_frames)   # bank capacity floor: 24 frames hold a 115-frame clip at memorize_every = 5
         self.last_bboxes = None   # [(prev_bbox, curr_bbox)] of the last clip (keep_bboxes=True), for inspection / tests
         self.last_logits = None   # [logit [1,K,H,W]] of the last clip (keep_logits=True): the return values of RMNet.segment + overrides
@@ -135,14 +136,16 @@ class RegionalFrameLoop:
     # ------------------------------------------------------------------------------------------------------------
     def _state(self, n, K, H, W, n_commits, dev):
         key = (n, K, H, W, dev.index)
-        st = self._states.get(key)
+        st = self._states.pop(key, None)                 # (re-inserted below: the dict is kept in least-recently-used order)
         if st is None or st.max_frames < n_commits + 1:
             # capacity in whole multiples of 8 frames so that clips of similar length reuse the bank and its graphs
             cap = max(self.min_bank_frames, ((n_commits + 1 + 7) // 8) * 8)
             st = _ClipState(self, n, K, H, W, cap, dev)
-            self._states[key] = st
         else:
             st.rm.bank.reset()
+        self._states[key] = st
+        while len(self._states) > self.max_cached_states:   # each state holds a bank and the graphs' private memory pool
+            self._states.pop(next(iter(self._states)))
         return st
 
     def _frame_body(self, st, commit, modes, new_mask, want_logit):
