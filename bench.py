@@ -540,7 +540,7 @@ def run_gpu(args, wl, rank, world, local_rank):
     h, w, lw, Wp = pool["h"], pool["w"], pool["lw"], pool["Wp"]
     N = h * w
     frames = pool["frames"]
-    precision = rmnet_b200.RMNET_PREC_SINGLE if args.precision == "single" else rmnet_b200.RMNET_PREC_SPLIT3
+    precision = {"single": rmnet_b200.RMNET_PREC_SINGLE, "mixed": rmnet_b200.RMNET_PREC_MIXED}.get(args.precision, rmnet_b200.RMNET_PREC_SPLIT3)
     rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T, device=dev, precision=precision)
 
     def to_dev(fr):
@@ -622,6 +622,32 @@ def run_gpu(args, wl, rank, world, local_rank):
     if os.environ.get("RMNET_BENCH_DEBUG"):
         med = float(np.median(step_ms))
         print("step outliers (idx:ms):", " ".join(f"{i}:{t:.3f}" for i, t in enumerate(step_ms) if t > 2 * med), file=sys.stderr)
+
+    # ---- the other precision modes of the read kernel on the same bank and inputs (rank 0; the bank's fp16 hi/lo planes serve
+    #      all three: strict = 3 products for both GEMMs, mixed = 3 for Q.K^T + 1 for P.V, fast = 1 + 1), device time per step
+    modes_info = None
+    if rank == 0:
+        modes_info = {}
+        keep = rm.precision
+        for name, prec in (("split3", rmnet_b200.RMNET_PREC_SPLIT3), ("mixed", rmnet_b200.RMNET_PREC_MIXED), ("single", rmnet_b200.RMNET_PREC_SINGLE)):
+            rm.precision = prec
+            for i in range(3):
+                step_dev(dframes[i % len(dframes)])
+            mev = []
+            for i in range(min(args.steps, 50)):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                step_dev(dframes[i % len(dframes)])
+                b.record()
+                mev.append((a, b))
+            torch.cuda.synchronize()
+            ms = float(np.mean([a.elapsed_time(b) for a, b in mev]))
+            modes_info[name] = {"ms_per_step": ms, "frames_per_s": 1e3 / ms}
+        rm.precision = keep
+        modes_info["logit_error_under_the_real_decoder"] = (
+            "max-abs on RMNet.segment's logit map vs the unmodified model, default-init weights (|score| 642) / conditioned: strict 1.1e-5 / 1.4e-5, "
+            "mixed 3.8e-4 / 1.2e-5, fast 3.9e-3 / 3.5e-4 (tests/test_gpu_rmnet.py; north_star's bound: 1e-3)")
 
     # ---- the same step captured once as a CUDA graph (RegionalMemory.capture_step) and replayed: device time per step and
     #      the host time per step of both submission paths (enqueue only, measured over a batch with one sync at the end)
@@ -711,7 +737,8 @@ def run_gpu(args, wl, rank, world, local_rank):
     rq_h = rq.cpu().numpy()
     nq = [max(0, int(r[1] - r[0] + 1)) * max(0, int(r[3] - r[2] + 1)) for r in rq_h]
     flops, byts = algorithmic_work(cells.tolist(), nq, N)
-    passes = 1 if args.precision == "single" else 3
+    # tensor-core products per MAC of the algorithmic flops: strict 3, fast 1, mixed = 3 for Q.K^T (128 of the 640 channels) and 1 for P.V
+    passes = {"single": 1.0, "mixed": (3.0 * 128 + 512) / 640}.get(args.precision, 3.0)
     d0 = dframes[0]
     rm.bank.read(d0["qk"], d0["qv"], rq, n, precision, out=m4)   # all stages once: the query side of d0 is now in the workspace
     kt, mt = [], []
@@ -814,7 +841,8 @@ def run_gpu(args, wl, rank, world, local_rank):
         "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(np.max(step_ms)),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16 hi/lo split x3, fp32 accumulate" if passes == 3 else "bf16 x1, fp32 accumulate", "data": "synthetic",
+        "dtype": {"split3": "fp16 hi/lo planes x3 products, fp32 accumulate", "single": "fp16 x1 product, fp32 accumulate",
+                  "mixed": "fp16 hi/lo x3 products for Q.K^T, x1 for P.V, fp32 accumulate"}[args.precision], "data": "synthetic",
         "config": {"workload": f"{args.workload}: {wl['desc']}; one step = one frame of the regional memory-read path "
                                "(both region descriptors -> pack-at-memorise + query side -> tcgen05 regional read of all objects -> merge; "
                                "4 kernels chained by programmatic dependent launch: RegionalMemory.step)",
@@ -824,7 +852,7 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "e2e_workload": f"{VOS_CLIPS_PER_GPU} clips per GPU, {VOS_SHAPE['H']}x{VOS_SHAPE['W']}, {VOS_SHAPE['n']} objects, F={VOS_SHAPE['F']}, "
                                    f"memorize_every={VOS_SHAPE['every']}, K={K_CH}; sharded longest-first, each rank pinned to its own host cores ({core_slice})"},
         "e2e": e2e, "e2e_op": e2e_op, "vos": vos_extra,
-        "gpu_launches": launches, "cuda_graph": graph_info, "reference_on_this_gpu": ref_gpu, "roofline": roof, "clocks": clk, "result_checksums": sums,
+        "gpu_launches": launches, "cuda_graph": graph_info, "precision_modes": modes_info, "reference_on_this_gpu": ref_gpu, "roofline": roof, "clocks": clk, "result_checksums": sums,
     }
     return line, pool
 
@@ -838,7 +866,7 @@ def main():
     # c2 is BASELINE configs[1] (3 objects, T=5)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="split3", choices=["split3", "single"])
+    ap.add_argument("--precision", default="split3", choices=["split3", "single", "mixed"])
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-vos", action="store_true", help="skip the VOS e2e leg (op-level legs only)")
     ap.add_argument("--no-vos-extras", action="store_true", help="skip the F=100 clip / reference-on-this-GPU / module split")

@@ -51,6 +51,7 @@ extern "C" {
 /* precision modes of the memory read (see DESIGN.md "precision") */
 #define RMNET_PREC_SPLIT3 0 /* strict: 16-bit hi/lo split operands, 3 tensor-core products per GEMM, fp32 accumulate */
 #define RMNET_PREC_SINGLE 1 /* fast:   hi planes only, 1 product per GEMM                                            */
+#define RMNET_PREC_MIXED 2  /* mixed:  3 products for the scores Q.K^T (their error is exponentiated), 1 for P.V        */
 /* kernel selection (both are sm_100a CUDA; there is no CPU fallback) */
 #define RMNET_IMPL_AUTO 0
 #define RMNET_IMPL_SIMT 1   /* CUDA-core fp32 FFMA flash kernel (cross-check / odd shapes) */

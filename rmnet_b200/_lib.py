@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librmnet_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-RMNET_PREC_SPLIT3, RMNET_PREC_SINGLE = 0, 1
+RMNET_PREC_SPLIT3, RMNET_PREC_SINGLE, RMNET_PREC_MIXED = 0, 1, 2
 RMNET_IMPL_AUTO, RMNET_IMPL_SIMT, RMNET_IMPL_UMMA = 0, 1, 2
 ELEM_BF16, ELEM_FP16 = 0, 1
 SAMPLER_CUDNN, SAMPLER_ATEN = 0, 1

@@ -46,7 +46,7 @@ int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int 
   RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
   RMNET_CHECK_ARG(n_obj <= 65535, "too many objects");
   RMNET_CHECK_ARG(elem_format == 0 || elem_format == 1, "elem_format must be 0 (bf16) or 1 (fp16)");
-  RMNET_CHECK_ARG(precision == RMNET_PREC_SPLIT3 || precision == RMNET_PREC_SINGLE, "bad precision mode");
+  RMNET_CHECK_ARG(precision == RMNET_PREC_SPLIT3 || precision == RMNET_PREC_SINGLE || precision == RMNET_PREC_MIXED, "bad precision mode");
   RMNET_CHECK_ARG(q_rects == nullptr || (uintptr_t)q_rects % 16 == 0, "q_rects must be 16-byte aligned");
   BankLayout L = bank_layout(n_slots, cap_cells);
   if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }

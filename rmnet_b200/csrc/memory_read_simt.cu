@@ -191,7 +191,7 @@ int launch_memory_read_simt(const BankView &bank, const float *q_key, long long 
                                   (int)sizeof(SimtSmem)));
   dim3 grid(cdiv(h * w, QT), n_obj, 2 * n_splits);
   memory_read_simt_kernel<<<grid, kThreads, sizeof(SimtSmem), st>>>(
-      bank, q_key, q_obj_stride, q_rects, h, w, fmt, precision == RMNET_PREC_SPLIT3 ? 1 : 0, n_splits, W.opart, W.ml,
+      bank, q_key, q_obj_stride, q_rects, h, w, fmt, precision != RMNET_PREC_SINGLE ? 1 : 0  /* the FFMA cross-check kernel has no mixed mode: it runs MIXED as strict */, n_splits, W.opart, W.ml,
       W.nq_pad, n_obj);
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;

@@ -191,7 +191,10 @@ struct PieceIter {
   }
 };
 
-template <int FMT, bool USE_LO>
+// USE_LO: the score product Q.K^T takes the 3-term hi/lo split (K lo plane loaded, Q lo plane in TMEM);
+// PV_LO : so does the P.V product (V lo plane loaded, P split into hi/lo).  (true, true) = strict, (false, false) = fast,
+// (true, false) = mixed: scores -- whose error is exponentiated -- keep 22 mantissa bits, P and V go through one product.
+template <int FMT, bool USE_LO, bool PV_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
@@ -224,6 +227,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   if (tstamp && threadIdx.x == 128) tstamp[0] = clock64();
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
+  constexpr bool pv_lo = PV_LO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1).
@@ -307,11 +311,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
           mbar_wait(smem_u32(&bars->v_empty[s]), ((vt / VST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->v_full[s]);
           if ((dbg_flags & 1) && vt >= VST) { mbar_arrive(full); continue; }
-          mbar_expect_tx(full, use_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
+          mbar_expect_tx(full, pv_lo ? V_STAGE_BYTES : V_PLANE_BYTES);
           const uint32_t dst = v_smem + s * V_STAGE_BYTES;
           const int m0 = (pc.tile_begin + it) * MT;
           tma_load_3d(dst, &map_vhi, full, m0, pc.half * CVH, pc.o);
-          if (use_lo) tma_load_3d(dst + V_PLANE_BYTES, &map_vlo, full, m0, pc.half * CVH, pc.o);
+          if (pv_lo) tma_load_3d(dst + V_PLANE_BYTES, &map_vlo, full, m0, pc.half * CVH, pc.o);
         }
       }
     }
@@ -367,7 +371,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
             for (int kk = 0; kk < MT / 16; ++kk) {
               const uint64_t bh = umma_desc_sw128(vb + kk * 32);
               umma_ts(tmem + TM_O, p_hi + kk * 8, bh, idesc_pv, (it > 0 || kk > 0) ? 1u : 0u);
-              if (use_lo) {
+              if (pv_lo) {
                 const uint64_t bl = umma_desc_sw128(vb + V_PLANE_BYTES + kk * 32);
                 umma_ts(tmem + TM_O, p_hi + kk * 8, bl, idesc_pv, 1u);
                 umma_ts(tmem + TM_O, p_lo + kk * 8, bh, idesc_pv, 1u);
@@ -541,10 +545,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
             l0 += p0;
             l1 += p1;
             pl[j] = 0;
-            split_pack2<FMT, USE_LO>(p0, p1, ph[j], pl[j]);
+            split_pack2<FMT, PV_LO>(p0, p1, ph[j], pl[j]);
           }
           TMEM_ST8(s_addr + c / 2, ph, 0);
-          if (USE_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
+          if (PV_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
         }
         l_sum += l0 + l1;
         tc_wait_st();
@@ -651,25 +655,27 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
   const int n_sms = umma_grid_size();
   dim3 grid(n_sms);
   (void)n_splits;
-  const bool lo = precision == RMNET_PREC_SPLIT3;
-#define RMNET_LAUNCH_UMMA(F, L)                                                                                          \
+  const bool lo = precision != RMNET_PREC_SINGLE, plo = precision == RMNET_PREC_SPLIT3;
+#define RMNET_LAUNCH_UMMA(F, L, P)                                                                                          \
   do {                                                                                                                   \
     static bool attr_set[64] = {};                                                                                       \
     int dev_ = 0;                                                                                                        \
     RMNET_CUDA(cudaGetDevice(&dev_));                                                                                    \
     if (dev_ < 0 || dev_ >= 64 || !attr_set[dev_]) {                                                                     \
-      RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+      RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)SMEM_BYTES));                                                                 \
       if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                                 \
     }                                                                                                                    \
-    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
+    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L, P>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
                              bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
                              temp_rects, bank.cap, g_dbg, g_dbg_flags));                                                 \
   } while (0)
-  if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true);
-  else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false);
-  else if (lo) RMNET_LAUNCH_UMMA(1, true);
-  else RMNET_LAUNCH_UMMA(1, false);
+  if (fmt == 0 && plo) RMNET_LAUNCH_UMMA(0, true, true);
+  else if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true, false);
+  else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false, false);
+  else if (plo) RMNET_LAUNCH_UMMA(1, true, true);
+  else if (lo) RMNET_LAUNCH_UMMA(1, true, false);
+  else RMNET_LAUNCH_UMMA(1, false, false);
 #undef RMNET_LAUNCH_UMMA
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;

@@ -399,7 +399,8 @@ def test_regional_path_vs_oracle_with_temp_and_commit(impl_name, impl, cfg):
 
 
 @pytest.mark.parametrize("fmt_name,fmt", [("bf16", rmnet_b200.ELEM_BF16), ("fp16", rmnet_b200.ELEM_FP16)])
-@pytest.mark.parametrize("prec_name,prec,tol", [("split3", rmnet_b200.RMNET_PREC_SPLIT3, TOL_STRICT), ("single", rmnet_b200.RMNET_PREC_SINGLE, TOL_FAST)])
+@pytest.mark.parametrize("prec_name,prec,tol", [("split3", rmnet_b200.RMNET_PREC_SPLIT3, TOL_STRICT), ("mixed", rmnet_b200.RMNET_PREC_MIXED, 2e-3),
+                                                ("single", rmnet_b200.RMNET_PREC_SINGLE, TOL_FAST)])
 def test_umma_formats_and_precisions(fmt_name, fmt, prec_name, prec, tol):
     """Both 16-bit plane formats (instruction-descriptor bit) and both precision modes of the tcgen05 kernel."""
     if not _impl_available(rmnet_b200.RMNET_IMPL_UMMA):

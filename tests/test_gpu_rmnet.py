@@ -163,14 +163,16 @@ def test_fast_precision_mode_logit_error_is_reported_and_bounded(name):
     est_ref, logit_ref, boxes_ref, max_score = _run_reference(ref, net, frames, masks, flows, n_objects, every)
     est_ref = est_ref.to(DEV)
     out = {}
-    for mode, prec in (("strict", rmnet_b200.RMNET_PREC_SPLIT3), ("fast", rmnet_b200.RMNET_PREC_SINGLE)):
+    for mode, prec in (("strict", rmnet_b200.RMNET_PREC_SPLIT3), ("mixed", rmnet_b200.RMNET_PREC_MIXED), ("fast", rmnet_b200.RMNET_PREC_SINGLE)):
         loop = rmnet_b200.RegionalFrameLoop.from_rmnet(net, precision=prec)
         loop.forward(frames, masks, flows, n_objects, every, teacher_masks=est_ref, keep_logits=True, keep_bboxes=True)
         out[mode] = max(float((a - b).abs().max()) for a, b in zip(loop.last_logits, logit_ref))
         for (pb, cb), (pb_r, cb_r) in zip(loop.last_bboxes, boxes_ref):
             assert torch.equal(pb.cpu(), pb_r.cpu()) and torch.equal(cb.cpu(), cb_r.cpu())
-    print(f"\n[{name}] max |scaled score| {max_score:.1f}: logit max-abs vs reference -- strict {out['strict']:.1e}, fast {out['fast']:.1e}")
+    print(f"\n[{name}] max |scaled score| {max_score:.1f}: logit max-abs vs reference -- strict {out['strict']:.1e}, "
+          f"mixed (scores x3, P.V x1) {out['mixed']:.1e}, fast {out['fast']:.1e}")
     assert out["strict"] <= LOGIT_TOL
+    assert out["mixed"] <= 5 * LOGIT_TOL
     assert out["fast"] <= 0.5
 
 
@@ -208,6 +210,31 @@ def test_install_runs_the_fused_loop_free_running_and_literal_multi_scale_infere
         ious.append(float((a & b).sum()) / max(1.0, float((a | b).sum())))
     print(f"\nfree-running IoU per label {ious}; max |est_probs - reference| {float((probs.cpu() - probs_ref.cpu()).abs().max()):.2e}")
     assert min(ious) >= 0.99
+
+
+def test_installed_forward_with_host_inputs_and_an_explicit_device_like_the_eval_server():
+    """utils/eval_server.py:106-107 calls the bare network with HOST tensors and an explicit device:
+    network(frames, masks, optical_flows, n_objects, MEMORIZE_EVERY, device).  Same call on the unmodified and on the
+    installed model: same return type / device (a host tensor, models/rmnet.py:388-392), same masks."""
+    ref = _need_reference()
+    _strict_backend()
+    H, W, n, F_ = 240, 432, 2, 6
+    _, net = baseline.build_nets(3, DEV, conditioned=True, cpu_generator=False, with_flownet=False)
+    frames, masks, n_objects = baseline.synthetic_clip(21, n, F_, H, W)
+    flows = torch.randn((1, F_, 2, H, W), generator=torch.Generator().manual_seed(2)) * 1.5
+    dev = torch.device(DEV)
+    rmnet_b200.uninstall(ref)
+    with torch.no_grad():
+        want = net(frames, masks, flows, n_objects, 2, dev)
+    rmnet_b200.install(ref)
+    try:
+        with torch.no_grad():
+            got = net(frames, masks, flows, n_objects, 2, dev)
+    finally:
+        rmnet_b200.uninstall(ref)
+    assert got.device == want.device and got.shape == want.shape and got.dtype == want.dtype
+    assert float((got - want).abs().max()) <= 1e-3
+    assert float((got.argmax(2) == want.argmax(2)).float().mean()) >= 0.999
 
 
 def test_fused_forward_falls_back_to_the_reference_forward_for_training_calls():
