@@ -376,6 +376,12 @@ def run_vos(args, rank, world, local_rank, dev, precision):
     H, W, n, F_, every = (VOS_SHAPE[k] for k in ("H", "W", "n", "F", "every"))
     n_clips = VOS_CLIPS_PER_GPU * world
     clips = [dict(seed=5000 + i, n=n, F=F_) for i in range(n_clips)]
+    if args.e2e_set == "davis30":
+        # BASELINE configs[2] as SURVEY 8d spells it out: 30 clips with the DAVIS-2017 val clip lengths (34..104 frames, 1 999 in
+        # total; read from the reference's own datasets/DAVIS.json), 480x854, object counts cycling 1..5, sharded longest-first
+        lengths = [v["n_frames"] for v in json.load(open(os.path.join(baseline.ref_root(), "datasets", "DAVIS.json")))["val"]]
+        clips = [dict(seed=6000 + i, n=1 + i % 5, F=f) for i, f in enumerate(lengths)]
+        n_clips = len(clips)
     mine = shard_longest_first([c["F"] * c["n"] for c in clips], world)[rank]
     L = rmnet_b200.lib()
 
@@ -387,8 +393,9 @@ def run_vos(args, rank, world, local_rank, dev, precision):
         return probs[0].to(dev).argmax(1).to(torch.uint8)                             # core/inference.py:61 (on the device: 270 M floats)
 
     # warm-up: one short clip of the same shape (cuDNN plans, graph capture of the frame body)
-    wf, wm, wn = baseline.synthetic_clip(4999, n, 8, H, W)
-    vos.run_clip(tfn_dp, net_dp, wf, wm, wn, every)
+    for n_w in sorted({clips[ci]["n"] for ci in mine}):
+        wf, wm, wn = baseline.synthetic_clip(4999, n_w, 8, H, W)
+        vos.run_clip(tfn_dp, net_dp, wf, wm, wn, every)
     loop = net.__dict__["_rmnet_b200_loop"]
     L.rmnet_launch_count_reset()
     g0 = loop.graph_launches
@@ -418,8 +425,12 @@ def run_vos(args, rank, world, local_rank, dev, precision):
     gathered = None
     if world > 1:
         import torch.distributed as dist
-        stack = torch.stack(labs)                                                     # [clips, F, H, W] uint8
-        gather_label_maps(stack[:1, :1].contiguous(), rank, world)                    # untimed: NCCL sets its channels up on first use
+        stack = torch.cat(labs)                                                       # [frames of this rank's clips, H, W] uint8
+        nf = torch.tensor([stack.shape[0]], device=dev, dtype=torch.int64)
+        dist.all_reduce(nf, op=dist.ReduceOp.MAX)                                     # ranks may hold different frame totals (davis30)
+        if int(nf) > stack.shape[0]:
+            stack = torch.cat([stack, stack.new_zeros((int(nf) - stack.shape[0],) + tuple(stack.shape[1:]))])
+        gather_label_maps(stack[:1].contiguous(), rank, world)                        # untimed: NCCL sets its channels up on first use
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         outs = gather_label_maps(stack, rank, world)                                  # the one collective of the job
@@ -428,7 +439,8 @@ def run_vos(args, rank, world, local_rank, dev, precision):
         secs += gather_s
         if rank == 0:
             gathered = [int(o.numel()) for o in outs]
-    info = {"clips_total": n_clips, "clips_this_rank": len(mine), "frames_per_clip": F_, "objects": n, "memorize_every": every,
+    info = {"clips_total": n_clips, "clips_this_rank": len(mine), "frames_per_clip": F_ if args.e2e_set == "default" else "DAVIS-2017 val lengths (34..104)",
+            "objects": n if args.e2e_set == "default" else "1..5 cycling", "memorize_every": every, "set": args.e2e_set,
             "flownet_share": flow_s / max(secs, 1e-9), "gather_s": gather_s, "gathered_label_bytes": gathered,
             "launches": launches, "h2d_bytes_per_frame": h2d / max(frames_done, 1), "d2h_bytes_per_frame": d2h / max(frames_done, 1),
             "allow_tf32_convs": bool(torch.backends.cudnn.allow_tf32), "graph": bool(loop.use_graph),
@@ -849,8 +861,10 @@ def run_gpu(args, wl, rank, world, local_rank):
                    "clips_per_gpu": 1, "parallelism": f"clip-parallel x{world} (no data-path collective; one NCCL gather of the label maps in the e2e leg)",
                    "precision": args.precision,
                    "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed", "pool_frames": POOL,
-                   "e2e_workload": f"{VOS_CLIPS_PER_GPU} clips per GPU, {VOS_SHAPE['H']}x{VOS_SHAPE['W']}, {VOS_SHAPE['n']} objects, F={VOS_SHAPE['F']}, "
-                                   f"memorize_every={VOS_SHAPE['every']}, K={K_CH}; sharded longest-first, each rank pinned to its own host cores ({core_slice})"},
+                   "e2e_workload": (f"{VOS_CLIPS_PER_GPU} clips per GPU, {VOS_SHAPE['H']}x{VOS_SHAPE['W']}, {VOS_SHAPE['n']} objects, F={VOS_SHAPE['F']}, "
+                                    if args.e2e_set == "default" else
+                                    f"30 clips shaped like DAVIS-2017 val (BASELINE configs[2]): {VOS_SHAPE['H']}x{VOS_SHAPE['W']}, 1..5 objects cycling, 34..104 frames (1 999 in total), ")
+                                   + f"memorize_every={VOS_SHAPE['every']}, K={K_CH}; sharded longest-first, each rank pinned to its own host cores ({core_slice})"},
         "e2e": e2e, "e2e_op": e2e_op, "vos": vos_extra,
         "gpu_launches": launches, "cuda_graph": graph_info, "precision_modes": modes_info, "reference_on_this_gpu": ref_gpu, "roofline": roof, "clocks": clk, "result_checksums": sums,
     }
@@ -869,6 +883,8 @@ def main():
     ap.add_argument("--precision", default="split3", choices=["split3", "single", "mixed"])
     ap.add_argument("--cpu-steps", type=int, default=0, help="steps of the CPU baseline sample (0 = auto, ~10-30 s)")
     ap.add_argument("--no-vos", action="store_true", help="skip the VOS e2e leg (op-level legs only)")
+    ap.add_argument("--e2e-set", default="default", choices=["default", "davis30"],
+                    help="clips of the e2e leg: 8 per GPU, 5 objects, F=60 (default) | the 30 DAVIS-val-shaped clips of BASELINE configs[2]")
     ap.add_argument("--no-vos-extras", action="store_true", help="skip the F=100 clip / reference-on-this-GPU / module split")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
