@@ -1,5 +1,5 @@
 """GPU probe: VOS frames/s of the unmodified reference vs the installed path (eager / graph), per-module split.
-usage: python tools/vos_probe.py [workload] [frames] [every]"""
+usage: python tools/vos_probe.py [workload] [frames] [every] [lean]"""
 import json
 import os
 import sys
@@ -51,7 +51,13 @@ def our_leg(graph, output="reference"):
             rmnet_b200.uninstall(ref)
     return f
 
+lean = len(sys.argv) > 4 and sys.argv[4] == "lean"     # reference + the default installed path only (large workloads)
 leg("reference", ref_leg)
+if lean:
+    leg("ours_graph", our_leg(True))
+    res.pop("_ref_lab", None)
+    print(json.dumps(res, indent=1))
+    sys.exit(0)
 leg("ours_eager", our_leg(False))
 leg("ours_graph", our_leg(True))
 leg("ours_graph_device", our_leg(True, "device"))
