@@ -816,7 +816,11 @@ def run_gpu(args, wl, rank, world, local_rank):
     del dflat, dbuf, obuf, flush
     torch.cuda.empty_cache()
     vos_s, vos_frames, vos_info, vos_extra = None, 0, None, None
-    if not args.no_vos:
+    import baseline
+    if not args.no_vos and not baseline.available():
+        # the same on every rank (the tree ships with the snapshot or not at all): no collective is entered
+        vos_info = {"error": "baseline/_ref (the reference tree) is not on this box: run __graft_entry__.build() in the build container"}
+    elif not args.no_vos:
         try:
             vos_s, vos_frames, vos_info, vos_extra = run_vos(args, rank, world, local_rank, dev, precision)
         except Exception as e:
