@@ -198,6 +198,7 @@ class CapturedStep:
 
 
 _ORIG = "_rmnet_b200_originals"
+_replica_loops = {}   # see fused_forward
 
 
 def fused_forward(self, frames, masks, optical_flows, n_objects, memorize_every, device=None):
@@ -210,11 +211,24 @@ def fused_forward(self, frames, masks, optical_flows, n_objects, memorize_every,
         return getattr(type(self), _ORIG)["forward"](self, frames, masks, optical_flows, n_objects, memorize_every, device)
     from .frame_loop import RegionalFrameLoop
     opts = getattr(type(self), "_rmnet_b200_options")
-    loop = self.__dict__.get("_rmnet_b200_loop")
-    if loop is None or loop._options is not opts:
-        loop = RegionalFrameLoop.from_rmnet(self, **opts)
-        loop._options = opts
-        object.__setattr__(self, "_rmnet_b200_loop", loop)
+    if getattr(self, "_is_replica", False):
+        # nn.DataParallel over several GPUs (core/inference.py:36-37 on a multi-GPU box) calls a fresh REPLICA of the model on
+        # every forward; its device-0 tensors alias the original parameters, so the loop (bank, captured graphs) is kept in
+        # a small module-level cache keyed by a parameter's storage instead of on the short-lived replica
+        key = (self.kv_memory.key_conv.weight.data_ptr(), id(opts))
+        loop = _replica_loops.pop(key, None)
+        if loop is None:
+            loop = RegionalFrameLoop.from_rmnet(self, **opts)
+            loop._options = opts
+        _replica_loops[key] = loop
+        while len(_replica_loops) > 2:
+            _replica_loops.pop(next(iter(_replica_loops)))
+    else:
+        loop = self.__dict__.get("_rmnet_b200_loop")
+        if loop is None or loop._options is not opts:
+            loop = RegionalFrameLoop.from_rmnet(self, **opts)
+            loop._options = opts
+            object.__setattr__(self, "_rmnet_b200_loop", loop)
     return loop.forward(frames, masks, optical_flows, n_objects, memorize_every, device)
 
 

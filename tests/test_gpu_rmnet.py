@@ -237,6 +237,39 @@ def test_installed_forward_with_host_inputs_and_an_explicit_device_like_the_eval
     assert float((got.argmax(2) == want.argmax(2)).float().mean()) >= 0.999
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two visible GPUs (nn.DataParallel replicates the model)")
+def test_install_under_multi_gpu_dataparallel_replicas_keeps_one_loop():
+    """core/inference.py:36-37 on a multi-GPU box: nn.DataParallel over ALL visible GPUs with batch 1 -> the forward runs on a
+    fresh replica of the model on GPU 0 every call.  The installed forward must give the reference's result there too and
+    must not rebuild its loop (bank, graphs) per call."""
+    ref = _need_reference()
+    import utils.helpers as ref_helpers
+    from rmnet_b200 import modules
+    _strict_backend()
+    H, W, n, F_ = 240, 432, 2, 8
+    tfn, net = baseline.build_nets(0, DEV, conditioned=True, cpu_generator=False)
+    cfg = baseline.test_cfg(memorize_every=3)
+    frames, masks, n_objects = baseline.synthetic_clip(9, n, F_, H, W)
+    tfn_dp, net_dp = torch.nn.DataParallel(tfn).cuda(), torch.nn.DataParallel(net).cuda()     # device_ids = all GPUs
+    rmnet_b200.uninstall(ref)
+    with torch.no_grad():
+        _, probs_ref = ref_helpers.multi_scale_inference(cfg, tfn_dp, net_dp, frames, masks, n_objects)
+    rmnet_b200.install(ref)
+    try:
+        modules._replica_loops.clear()
+        with torch.no_grad():
+            _, probs = ref_helpers.multi_scale_inference(cfg, tfn_dp, net_dp, frames, masks, n_objects)
+            loops = list(modules._replica_loops.values())
+            _, probs2 = ref_helpers.multi_scale_inference(cfg, tfn_dp, net_dp, frames, masks, n_objects)
+        assert len(loops) == 1 and list(modules._replica_loops.values())[0] is loops[0]
+    finally:
+        rmnet_b200.uninstall(ref)
+    assert probs.device == probs_ref.device and probs.shape == probs_ref.shape
+    assert float((probs.float().cpu() - probs_ref.float().cpu()).abs().max()) <= 1e-3
+    # (not bit-equal run to run: the per-channel value sums of the bank are float atomics, whose order is not fixed)
+    assert float((probs2.float().cpu() - probs.float().cpu()).abs().max()) <= 1e-5
+
+
 def test_fused_forward_falls_back_to_the_reference_forward_for_training_calls():
     ref = _need_reference()
     _, net = baseline.build_nets(0, DEV, cpu_generator=False, with_flownet=False)
