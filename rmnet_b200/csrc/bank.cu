@@ -208,8 +208,11 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
   }
   atomicAdd(&sm.vsum[cg + kGroups * lane], x[0]);  // the two warps of a channel group meet here
   __syncthreads();
+  // (sm.vsum[c] = 0 + a + b of the group's two warps: float addition is commutative, so the CTA partial is reproducible;
+  //  the cross-CTA accumulation is an integer atomic on the 2^-24 fixed-point image of the partial -- see BankView::vsum)
   if (threadIdx.x < kChunk)
-    atomicAdd(bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV + cbase + threadIdx.x, sm.vsum[threadIdx.x]);
+    atomicAdd(reinterpret_cast<unsigned long long *>(bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV + cbase + threadIdx.x),
+              (unsigned long long)__float2ll_rn(sm.vsum[threadIdx.x] * VSUM_SCALE));
 }
 
 // `keys = this_keys` (models/rmnet.py:424-426): the temporary frame becomes permanent.
@@ -218,8 +221,8 @@ __global__ void bank_commit_kernel(BankView bank, int n_obj) {
   pdl_trigger();
   const int o = blockIdx.x;
   if (o >= n_obj) return;
-  float *vc = bank.vsum + (size_t)o * RMNET_CV, *vt = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
-  for (int c = threadIdx.x; c < RMNET_CV; c += blockDim.x) { vc[c] += vt[c]; vt[c] = 0.f; }
+  long long *vc = bank.vsum + (size_t)o * RMNET_CV, *vt = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
+  for (int c = threadIdx.x; c < RMNET_CV; c += blockDim.x) { vc[c] += vt[c]; vt[c] = 0; }
   if (threadIdx.x == 0) {
     int *m = bank.meta + o * 8;
     m[META_CELLS_C] += m[META_CELLS_T];
@@ -290,7 +293,7 @@ int rmnet::bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int ca
   BankView bv = bank_view(bank, n_slots, cap_cells);
   // vsum of the temporary frame restarts from zero
   if (!chained)
-    RMNET_CUDA(cudaMemsetAsync(bv.vsum + (size_t)n_slots * RMNET_CV, 0, (size_t)n_slots * RMNET_CV * sizeof(float), st));
+    RMNET_CUDA(cudaMemsetAsync(bv.vsum + (size_t)n_slots * RMNET_CV, 0, (size_t)n_slots * RMNET_CV * sizeof(long long), st));
   // with a query side (rmnet_frame_step) the same launch also packs the query keys and writes the q_val passthrough
   QuerySide qs = {};
   if (query_side) qs = *query_side;

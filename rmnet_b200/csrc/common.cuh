@@ -97,7 +97,7 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 // ---- memory-bank blob layout (see bank.cu) -------------------------------------------------
-// [meta: n_slots x 8 i32][vsum: 2 x n_slots x 512 f32][K hi][K lo][V hi][V lo]; sections 1024 B aligned.
+// [meta: n_slots x 8 i32][vsum: 2 x n_slots x 512 i64 fixed point][K hi][K lo][V hi][V lo]; sections 1024 B aligned.
 struct BankLayout {
   int n_slots, cap;
   size_t off_meta, off_vsum, off_khi, off_klo, off_vhi, off_vlo, total;
@@ -108,7 +108,7 @@ static inline BankLayout bank_layout(int n_slots, int cap) {
   L.cap = cap;
   size_t o = 0;
   L.off_meta = o; o = align_up(o + (size_t)n_slots * 8 * sizeof(int), 1024);
-  L.off_vsum = o; o = align_up(o + (size_t)n_slots * 2 * RMNET_CV * sizeof(float), 1024);
+  L.off_vsum = o; o = align_up(o + (size_t)n_slots * 2 * RMNET_CV * sizeof(long long), 1024);
   size_t kplane = (size_t)n_slots * cap * RMNET_CK * 2;
   size_t vplane = (size_t)n_slots * cap * RMNET_CV * 2;
   L.off_khi = o; o = align_up(o + kplane, 1024);
@@ -121,10 +121,16 @@ static inline BankLayout bank_layout(int n_slots, int cap) {
 // meta ints per slot
 enum { META_CELLS_C = 0, META_CELLS_T = 1, META_ZEROS_C = 2, META_ZEROS_T = 3, META_FRAMES_C = 4, META_FRAMES_T = 5, META_OVERFLOW = 6, META_RANGE = 7 };
 
+constexpr float VSUM_SCALE = 16777216.0f;          // 2^24
+constexpr float VSUM_INV_SCALE = 1.0f / 16777216.0f;
 // Device view of a bank, passed by value to kernels.
 struct BankView {
   int *meta;            // [n_slots][8]
-  float *vsum;          // [2][n_slots][512]  (0 = committed frames, 1 = temporary frame): sum of stored V per channel
+  // [2][n_slots][512]  (0 = committed frames, 1 = temporary frame): sum of the stored V per channel, in 2^-24 FIXED POINT.
+  // The per-CTA partial sums (fp32, computed in a fixed order) are accumulated with integer atomics, which are
+  // associative: the totals -- and with them the uniform rows of mem_val -- are bit-reproducible from run to run, which
+  // float atomics are not.  Range: |sum| < 2^39 (fp16-range values of a whole bank stay below 2^31).
+  long long *vsum;
   uint16_t *khi, *klo;  // [n_slots][cap][128]
   uint16_t *vhi, *vlo;  // [n_slots][512][cap]
   int n_slots, cap;
@@ -134,7 +140,7 @@ static inline BankView bank_view(void *bank, int n_slots, int cap) {
   char *b = (char *)bank;
   BankView v;
   v.meta = (int *)(b + L.off_meta);
-  v.vsum = (float *)(b + L.off_vsum);
+  v.vsum = (long long *)(b + L.off_vsum);
   v.khi = (uint16_t *)(b + L.off_khi);
   v.klo = (uint16_t *)(b + L.off_klo);
   v.vhi = (uint16_t *)(b + L.off_vhi);

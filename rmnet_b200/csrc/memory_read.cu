@@ -113,7 +113,8 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   // read -> merge.  Each kernel's launch latency and independent prologue overlap its predecessor's tail.
   int rc = frame_regions_chain_head(prev_mask, flow, 1, K, H, W, sampler, prob_threshold, n_pts_threshold, n_bbox_loose_pixels,
                                     pad_l, pad_r, pad_t, pad_b, k_scan, mem_bb, mem_rc, cur_bb, cur_rc, box_workspace,
-                                    box_workspace_bytes, bv.vsum + (size_t)n_slots * RMNET_CV, n_slots * RMNET_CV, stream);
+                                    box_workspace_bytes, reinterpret_cast<float *>(bv.vsum + (size_t)n_slots * RMNET_CV),
+                                    2 * n_slots * RMNET_CV /* 4-byte words of the temporary frame's i64 value sums */, stream);
   if (rc) return rc;
   RMNET_CHECK_ARG(q_key && q_val && mem_val && read_workspace, "null pointer argument");
   RMNET_CHECK_ARG(impl == RMNET_IMPL_AUTO || impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);

@@ -55,8 +55,8 @@ merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n
     const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
     const int M = Z + meta[META_CELLS_C] + meta[META_CELLS_T];
     if (tid < kChPerCta) {
-      const float *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
-      s_uniform[tid] = (vs_c[c0 + tid] + vs_t[c0 + tid]) * (1.0f / (float)M);
+      const long long *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
+      s_uniform[tid] = (__ll2float_rn(vs_c[c0 + tid] + vs_t[c0 + tid]) * VSUM_INV_SCALE) * (1.0f / (float)M);
     }
     __syncthreads();
     const int lane = tid & 31, cl = tid >> 5;

@@ -119,6 +119,32 @@ def test_dense_reader_vs_fp64_oracle_across_score_magnitudes(scale, tol):
     assert err <= tol
 
 
+def test_frame_step_is_bit_reproducible_from_run_to_run():
+    """Two fresh banks, the same frames: mem_val and the boxes must be bit-identical (the reference pins cuDNN to
+    deterministic algorithms, runner.py:73-74).  The per-channel value sums behind the uniform rows are accumulated with
+    integer atomics on a fixed-point image (associative), everything else has a fixed order."""
+    import bench
+    wl = bench.WORKLOADS["c2"]
+    n, T, H, W = wl["n"], 3, wl["H"], wl["W"]
+    pool = bench.make_pool(dict(wl, T=T), 77, 2)
+    fr = [{k: torch.from_numpy(v).to(DEV) for k, v in f.items()} for f in pool["frames"]]
+    outs = []
+    for rep in range(3):
+        rm = rmnet_b200.RegionalMemory(n, (H, W), max_frames=T + 1, device=DEV)
+        for t in range(T - 1):
+            rm.memorize(fr[t]["k4"], fr[t]["v4"], fr[t]["mask"][None], commit=True)
+        res = []
+        for t, commit in ((T - 1, True), (T, False)):
+            c = fr[t]
+            m, pb, cb = rm.step(c["k4"], c["v4"], c["mask"][None], c["flow"][None], c["qk"], c["qv"], commit=commit)
+            res.append((m.clone(), pb.clone(), cb.clone()))
+        outs.append(res)
+    for rep in outs[1:]:
+        for (m, pb, cb), (m0, pb0, cb0) in zip(rep, outs[0]):
+            assert torch.equal(pb, pb0) and torch.equal(cb, cb0)
+            assert torch.equal(m, m0), f"mem_val differs between runs by {float((m - m0).abs().max()):.2e}"
+
+
 def test_bank_overflow_is_reported_by_stats():
     """A frame that does not fit behind the committed cells is dropped and flagged (bank.cu META_OVERFLOW); the Python
     wrappers guard the frame count, so force it through the bookkeeping and check that stats() raises."""
