@@ -52,7 +52,7 @@ int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int 
   if (bank_bytes < L.total) { set_error("bank too small"); return RMNET_E_WORKSPACE; }
   cudaStream_t st = (cudaStream_t)stream;
   BankView bv = bank_view(const_cast<void *>(bank), n_slots, cap_cells);
-  if (impl == RMNET_IMPL_AUTO) impl = umma_supported(cap_cells) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
+  if (impl == RMNET_IMPL_AUTO) impl = (umma_supported(cap_cells) && n_obj <= SCHED_MAX_OBJ) ? RMNET_IMPL_UMMA : RMNET_IMPL_SIMT;
   RMNET_CHECK_ARG(impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
   const int n_splits = impl == RMNET_IMPL_UMMA ? READ_MAX_SPLITS : pick_splits(n_obj, h * w, 64, cap_cells);
   ReadWorkspace W = read_workspace(workspace, n_obj, h * w, n_splits);
@@ -118,7 +118,7 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   if (rc) return rc;
   RMNET_CHECK_ARG(q_key && q_val && mem_val && read_workspace, "null pointer argument");
   RMNET_CHECK_ARG(impl == RMNET_IMPL_AUTO || impl == RMNET_IMPL_UMMA || impl == RMNET_IMPL_SIMT, "unknown impl %d", impl);
-  const bool umma = impl == RMNET_IMPL_UMMA || (impl == RMNET_IMPL_AUTO && umma_supported(cap_cells));
+  const bool umma = impl == RMNET_IMPL_UMMA || (impl == RMNET_IMPL_AUTO && umma_supported(cap_cells) && n_obj <= SCHED_MAX_OBJ);
   ReadWorkspace RW = rmnet::read_workspace(read_workspace, n_obj, (int)N, umma ? READ_MAX_SPLITS : pick_splits(n_obj, (int)N, 64, cap_cells));
   if (read_workspace_bytes < RW.total) { set_error("workspace too small: %zu < %zu", read_workspace_bytes, RW.total); return RMNET_E_WORKSPACE; }
   // the pack launch also prepares the query side (packed query keys, q_val passthrough) of this frame's read
