@@ -254,7 +254,7 @@ __device__ __forceinline__ int rect_pos(const int4 r, int i, int w) {
 // persistent CTAs, so CTAs that run side by side stream the SAME key/value tiles (one DRAM fetch, L2 hits for the rest).
 // ns(o) = ceil(nt(o) / c); the chunk length c is chosen among max_nt / k, k = 1..READ_MAX_SPLITS, to minimise
 // rounds(c) * c  (rounds = ceil(#items / #CTAs)), subject to the accumulation-chain bound c <= MAX_TILES_PER_SPLIT.
-enum { SCHED_MAX_OBJ = 32, UMMA_QT = 128 };
+enum { SCHED_MAX_OBJ = 64, UMMA_QT = 128 };
 struct SchedTable {
   int nt[SCHED_MAX_OBJ];         // KV tiles of object o
   int nqt[SCHED_MAX_OBJ];        // query tiles of object o

@@ -37,8 +37,7 @@ constexpr uint32_t K_STAGE_BYTES = 2 * K_PLANE_BYTES;       // hi + lo
 constexpr uint32_t V_PLANE_BYTES = CVH * MT * 2;            // 32 KB: [256 ch][64 cells]
 constexpr uint32_t V_STAGE_BYTES = 2 * V_PLANE_BYTES;
 constexpr uint32_t SMEM_TILES = KST * K_STAGE_BYTES + VST * V_STAGE_BYTES;  // 224 KB
-constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 768 /*barriers + the warpgroups' exchange slots*/;
-// (with the 784 B static schedule table this is 231 952 B of the 232 448 B a CTA may have)
+constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 // TMEM column map
 constexpr uint32_t TM_O = 0, TM_S0 = 256, TM_Q_HI = 384, TM_Q_LO = 448;
@@ -162,10 +161,8 @@ struct Barriers {
   uint64_t k_full[KST], k_empty[KST], v_full[VST], v_empty[VST];
   uint64_t s_full[2], p_full[2], pv_done[2], q_ready;
   uint32_t tmem_base;
-  float xch[QT];      // row statistics exchanged between the two softmax warpgroups (NWG = 2)
 };
 
-static_assert(sizeof(Barriers) <= 768, "Barriers must fit the tail of the dynamic shared memory");
 struct Piece {
   int o, qtile, half, tile_begin, n_it, slot;
 };
@@ -197,12 +194,8 @@ struct PieceIter {
 // USE_LO: the score product Q.K^T takes the 3-term hi/lo split (K lo plane loaded, Q lo plane in TMEM);
 // PV_LO : so does the P.V product (V lo plane loaded, P split into hi/lo).  (true, true) = strict, (false, false) = fast,
 // (true, false) = mixed: scores -- whose error is exponentiated -- keep 22 mantissa bits, P and V go through one product.
-// NWG: softmax warpgroups.  With 2, a query row is shared by two threads (warps w and w + 4: the same TMEM lane quarter),
-// each owning half of the columns of every S tile, of the O accumulator and of the Q row: the per-tile softmax latency --
-// what bounds the fast mode -- and the Q-load / drain phases are halved.  The pair agrees on the reference max through a
-// 64-thread named barrier with an OR reduction per tile (and a shared-memory exchange only when a rescale is due).
-template <int FMT, bool USE_LO, bool PV_LO, int NWG>
-__global__ void __launch_bounds__(128 + 128 * NWG, 1)
+template <int FMT, bool USE_LO, bool PV_LO>
+__global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
                         const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
@@ -248,10 +241,10 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     for (int i = 0; i < VST; ++i) { mbar_init(smem_u32(&bars->v_full[i]), 1); mbar_init(smem_u32(&bars->v_empty[i]), 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&bars->s_full[i]), 1);
-      mbar_init(smem_u32(&bars->p_full[i]), 128 * NWG);
+      mbar_init(smem_u32(&bars->p_full[i]), 128);
       mbar_init(smem_u32(&bars->pv_done[i]), 1);
     }
-    mbar_init(smem_u32(&bars->q_ready), 128 * NWG);
+    mbar_init(smem_u32(&bars->q_ready), 128);
     fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: all 512 columns (one CTA per SM: the smem footprint guarantees it)
@@ -395,56 +388,29 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     }
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue warpgroup: thread <-> query row <-> TMEM lane =================
-    const int row = (threadIdx.x - 128) & (QT - 1);     // 0..127
-    const int wg = (threadIdx.x - 128) >> 7;            // softmax warpgroup: owns columns [wg * H, wg * H + H) of every tile
-    constexpr int H = MT / NWG;                         // score columns per thread
-    constexpr int OC = CVH / NWG;                       // O columns per thread (lazy rescale, drain)
-    constexpr int QW = (RMNET_CK / 2) / NWG;            // packed Q words per thread and plane
-    const bool stamp = row == 0 && wg == 0;
+    const int row = threadIdx.x - 128;                  // 0..127
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const uint32_t t_base = tmem + lane_base;
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
-    const int pair_bar = 1 + (warp & 3);                // named barrier of the two warps that share 32 rows
-    auto pair_sync = [&]() { if (NWG == 2) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory"); };
-    auto pair_any = [&](bool v) -> bool {               // warp-uniform OR over the pair's 64 threads
-      if (NWG == 1) return __any_sync(0xffffffffu, v);
-      uint32_t r;
-      asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.or.pred p, %2, 64, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(r) : "r"((uint32_t)v), "r"(pair_bar) : "memory");
-      return r != 0;
-    };
-    // max of a value over the row's two threads, identical on both (one 512 B exchange array: wg 1 posts, wg 0 combines and
-    // posts the result back)
-    auto pair_max = [&](float v) -> float {
-      if (NWG == 1) return v;
-      if (wg == 1) bars->xch[row] = v;
-      pair_sync();
-      if (wg == 0) { v = fmaxf(v, bars->xch[row]); bars->xch[row] = v; }
-      pair_sync();
-      if (wg == 1) v = bars->xch[row];
-      pair_sync();   // the slot may be overwritten by the next exchange only after wg 1 has read it
-      return v;
-    };
     int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
     bool first_piece = true;
     if (early) pdl_wait();  // the packed query keys (and, through the barriers, everything downstream) need the pack kernel
     pdl_trigger();          // after the wait: the merge kernel's pre-wait part relies on the bank being final
-    // this row's query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's query role in
-    // the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that each of the loads
-    // below is one coalesced 512 B access per warp; warpgroup wg fetches the 16-byte chunks [wg * 16 / NWG, ...)
-    uint32_t qh[QW], ql[USE_LO ? QW : 1];
+    // this row's 128 query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's
+    // query role in the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that
+    // each of the loads below is one coalesced 512 B access per warp
+    uint32_t qh[RMNET_CK / 2], ql[USE_LO ? RMNET_CK / 2 : 1];
     auto fetch_q = [&](const Piece &p) {
       const size_t r = ((size_t)p.o * nq_pad + p.qtile * QT + (row & ~31)) * (RMNET_CK / 8) + (row & 31);  // uint4 units
-      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r + (size_t)wg * (QW / 4) * 32;
-      const uint4 *pl = reinterpret_cast<const uint4 *>(qlo) + r + (size_t)wg * (QW / 4) * 32;
+      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r, *pl = reinterpret_cast<const uint4 *>(qlo) + r;
 #pragma unroll
-      for (int j = 0; j < QW / 4; ++j) {
+      for (int j = 0; j < RMNET_CK / 8; ++j) {
         const uint4 v = __ldg(ph + j * 32);
         qh[4 * j] = v.x; qh[4 * j + 1] = v.y; qh[4 * j + 2] = v.z; qh[4 * j + 3] = v.w;
       }
       if (USE_LO) {
 #pragma unroll
-        for (int j = 0; j < QW / 4; ++j) {
+        for (int j = 0; j < RMNET_CK / 8; ++j) {
           const uint4 v = __ldg(pl + j * 32);
           ql[4 * j] = v.x; ql[4 * j + 1] = v.y; ql[4 * j + 2] = v.z; ql[4 * j + 3] = v.w;
         }
@@ -456,53 +422,52 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     Piece nxt;
     bool have_cur = false, have_nxt = iter.next(nxt);
     int gt_done = 0;  // tile counter at the end of the current piece (parity of its last pv_done)
-    if (tstamp && stamp) tstamp[12] = clock64();
+    if (tstamp && row == 0) tstamp[12] = clock64();
     for (;;) {
       if (have_nxt) {
         // ---- Q rows of the next piece -> 16-bit hi/lo planes in TMEM (A operand of the score product).  All score
         //      MMAs of the current piece have retired (its last softmax pass waited on their commit) and its P.V
         //      MMAs do not read Q.
         fetch_q(nxt);
-        if (tstamp && first_piece && stamp) tstamp[13] = clock64();
+        if (tstamp && first_piece && row == 0) tstamp[13] = clock64();
 #pragma unroll
-        for (int c = 0; c < QW; c += 16) {
-          TMEM_ST16(t_base + TM_Q_HI + wg * QW + c, qh, c);
-          if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + wg * QW + c, ql, c);
+        for (int c = 0; c < RMNET_CK / 2; c += 16) {
+          TMEM_ST16(t_base + TM_Q_HI + c, qh, c);
+          if (USE_LO) TMEM_ST16(t_base + TM_Q_LO + c, ql, c);
         }
-        if (tstamp && first_piece && stamp) tstamp[14] = clock64();
+        if (tstamp && first_piece && row == 0) tstamp[14] = clock64();
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->q_ready));
-        if (tstamp && first_piece && stamp) tstamp[2] = clock64();
+        if (tstamp && first_piece && row == 0) tstamp[2] = clock64();
       }
       if (have_cur) {
         // ---- epilogue of the current piece: unnormalised numerators for merge.cu, partial slot pc.slot
         const int n = pc.qtile * QT + row;
         mbar_wait(smem_u32(&bars->pv_done[(gt_done - 1) & 1]), ((gt_done - 1) >> 1) & 1);
         tc_fence_after();
-        if (tstamp && first_piece && stamp) tstamp[5] = clock64();
-        float *ob = opart + (((size_t)pc.slot * n_obj + pc.o) * RMNET_CV + pc.half * CVH + wg * OC) * nq_pad + n;
-        const uint32_t o_base = t_base + TM_O + wg * OC;
+        if (tstamp && first_piece && row == 0) tstamp[5] = clock64();
+        float *ob = opart + (((size_t)pc.slot * n_obj + pc.o) * RMNET_CV + pc.half * CVH) * nq_pad + n;
         // software pipeline over 32-column groups: the TMEM load of group g+1 is in flight while group g is stored
         uint32_t ra[32], rb[32];
-        TMEM_LD16(o_base, ra, 0);
-        TMEM_LD16(o_base + 16, ra, 16);
+        TMEM_LD16(t_base + TM_O, ra, 0);
+        TMEM_LD16(t_base + TM_O + 16, ra, 16);
 #pragma unroll 1
-        for (int c = 0; c < OC; c += 64) {
+        for (int c = 0; c < CVH; c += 64) {
           tc_wait_ld();
-          TMEM_LD16(o_base + c + 32, rb, 0);
-          TMEM_LD16(o_base + c + 48, rb, 16);
+          TMEM_LD16(t_base + TM_O + c + 32, rb, 0);
+          TMEM_LD16(t_base + TM_O + c + 48, rb, 16);
 #pragma unroll
           for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(ra[j]);  // lanes run along queries: coalesced
           tc_wait_ld();
-          if (c + 64 < OC) {
-            TMEM_LD16(o_base + c + 64, ra, 0);
-            TMEM_LD16(o_base + c + 80, ra, 16);
+          if (c + 64 < CVH) {
+            TMEM_LD16(t_base + TM_O + c + 64, ra, 0);
+            TMEM_LD16(t_base + TM_O + c + 80, ra, 16);
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) ob[(c + 32 + j) * nq_pad] = __uint_as_float(rb[j]);
         }
-        if (tstamp && first_piece && stamp) tstamp[6] = clock64();
+        if (tstamp && first_piece && row == 0) tstamp[6] = clock64();
         first_piece = false;
       }
       if (!have_nxt) break;
@@ -518,51 +483,50 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         const uint32_t s_addr = t_base + TM_S0 + b * MT;
         mbar_wait(smem_u32(&bars->s_full[b]), (gt >> 1) & 1);
         tc_fence_after();
-        uint32_t sr[H];
-#pragma unroll
-        for (int c = 0; c < H; c += 16) TMEM_LD16(s_addr + wg * H + c, sr, c);
+        uint32_t sr[MT];
+        TMEM_LD16(s_addr, sr, 0);
+        TMEM_LD16(s_addr + 16, sr, 16);
+        TMEM_LD16(s_addr + 32, sr, 32);
+        TMEM_LD16(s_addr + 48, sr, 48);
         tc_wait_ld();
-        if (tstamp && first_piece && it == 0 && stamp) tstamp[3] = clock64();
+        if (tstamp && first_piece && it == 0 && row == 0) tstamp[3] = clock64();
         long long t_s1 = 0;
-        if (tstamp && first_piece && it == 1 && stamp) t_s1 = clock64();  // dev: S of the second tile is in registers
+        if (tstamp && first_piece && it == 1 && row == 0) t_s1 = clock64();  // dev: S of the second tile is in registers
         if (dbg && first_piece && it == 0 && blockIdx.x == 0) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) dbg[row * MT + wg * H + j] = __uint_as_float(sr[j]);
+          for (int j = 0; j < MT; ++j) dbg[row * MT + j] = __uint_as_float(sr[j]);
         }
-        const int valid = count - (pc.tile_begin + it) * MT - wg * H;  // own columns >= valid are beyond the stored cells (last tile only)
-        if (valid < H) {
+        const int valid = count - (pc.tile_begin + it) * MT;  // columns >= valid are beyond the stored cells (last tile only)
+        if (valid < MT) {
 #pragma unroll
-          for (int j = 0; j < H; ++j) if (j >= valid) sr[j] = 0xff800000u;  // -inf
+          for (int j = 0; j < MT; ++j) if (j >= valid) sr[j] = 0xff800000u;  // -inf
         }
         float mx0 = __uint_as_float(sr[0]), mx1 = __uint_as_float(sr[1]);
 #pragma unroll
-        for (int j = 2; j < H; j += 2) {
+        for (int j = 2; j < MT; j += 2) {
           mx0 = fmaxf(mx0, __uint_as_float(sr[j]));
           mx1 = fmaxf(mx1, __uint_as_float(sr[j + 1]));
         }
-        float mx = fmaxf(mx0, mx1) * scale;  // scale > 0: max commutes with the scaling
+        const float mx = fmaxf(mx0, mx1) * scale;  // scale > 0: max commutes with the scaling
         if (it == 0) {
-          mx = pair_max(mx);  // the row maximum over both column halves
           m_ref = (mx == -INFINITY) ? 0.f : mx;
-        } else if (pair_any(mx > m_ref + kTau)) {
+        } else if (__any_sync(0xffffffffu, mx > m_ref + kTau)) {
           // lazy rescale of the O accumulator (rare after the first tiles): PV(it-1) must have retired, PV(it) cannot
           // start before this warp arrives on p_full below.
-          mx = pair_max(mx);
           mbar_wait(smem_u32(&bars->pv_done[(gt - 1) & 1]), ((gt - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = fmaxf(m_ref, mx);
           const float f = exp2f(m_ref - m_new);
-          const uint32_t o_base = t_base + TM_O + wg * OC;
 #pragma unroll 1
-          for (int c = 0; c < OC; c += 32) {
+          for (int c = 0; c < CVH; c += 32) {
             uint32_t orr[32];
-            TMEM_LD16(o_base + c, orr, 0);
-            TMEM_LD16(o_base + c + 16, orr, 16);
+            TMEM_LD16(t_base + TM_O + c, orr, 0);
+            TMEM_LD16(t_base + TM_O + c + 16, orr, 16);
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 32; ++j) orr[j] = __float_as_uint(__uint_as_float(orr[j]) * f);
-            TMEM_ST16(o_base + c, orr, 0);
-            TMEM_ST16(o_base + c + 16, orr, 16);
+            TMEM_ST16(t_base + TM_O + c, orr, 0);
+            TMEM_ST16(t_base + TM_O + c + 16, orr, 16);
           }
           l_sum *= f;
           m_ref = m_new;
@@ -572,7 +536,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         const float neg_m = -m_ref;
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < H; c += 16) {
+        for (int c = 0; c < MT; c += 16) {
           uint32_t ph[8], pl[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -583,30 +547,24 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
             pl[j] = 0;
             split_pack2<FMT, PV_LO>(p0, p1, ph[j], pl[j]);
           }
-          TMEM_ST8(s_addr + (wg * H + c) / 2, ph, 0);
-          if (PV_LO) TMEM_ST8(s_addr + MT / 2 + (wg * H + c) / 2, pl, 0);
+          TMEM_ST8(s_addr + c / 2, ph, 0);
+          if (PV_LO) TMEM_ST8(s_addr + MT / 2 + c / 2, pl, 0);
         }
         l_sum += l0 + l1;
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->p_full[b]));
-        if (tstamp && first_piece && it == 1 && stamp) tstamp[15] = clock64();
-        if (tstamp && first_piece && it == 1 && stamp) tstamp[14] = t_s1;
+        if (tstamp && first_piece && it == 1 && row == 0) tstamp[15] = clock64();
+        if (tstamp && first_piece && it == 1 && row == 0) tstamp[14] = t_s1;
       }
       gt_done = gt;
-      // (max, sum) statistics of the piece for merge.cu (the row sum of both column halves)
-      if (NWG == 2) {
-        if (wg == 1) bars->xch[row] = l_sum;
-        pair_sync();
-        if (wg == 0) l_sum += bars->xch[row];
-        pair_sync();
-      }
-      if (wg == 0) {
+      // (max, sum) statistics of the piece for merge.cu
+      {
         float2 *dst = reinterpret_cast<float2 *>(ml) + (((size_t)pc.slot * n_obj + o) * 2 + pc.half) * nq_pad + n;
         *dst = make_float2(m_ref, l_sum);
       }
-      if (dbg && first_piece && blockIdx.x == 0 && wg == 0) dbg[QT * MT + row] = m_ref;
-      if (tstamp && first_piece && stamp) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
+      if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
+      if (tstamp && first_piece && row == 0) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
       have_nxt = iter.next(nxt);
     }
   }
@@ -698,32 +656,26 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
   dim3 grid(n_sms);
   (void)n_splits;
   const bool lo = precision != RMNET_PREC_SINGLE, plo = precision == RMNET_PREC_SPLIT3;
-#define RMNET_LAUNCH_UMMA(F, L, P, G)                                                                                          \
+#define RMNET_LAUNCH_UMMA(F, L, P)                                                                                          \
   do {                                                                                                                   \
     static bool attr_set[64] = {};                                                                                       \
     int dev_ = 0;                                                                                                        \
     RMNET_CUDA(cudaGetDevice(&dev_));                                                                                    \
     if (dev_ < 0 || dev_ >= 64 || !attr_set[dev_]) {                                                                     \
-      RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L, P, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+      RMNET_CUDA(cudaFuncSetAttribute(memory_read_umma_kernel<F, L, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                       (int)SMEM_BYTES));                                                                 \
       if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                                 \
     }                                                                                                                    \
-    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L, P, G>, grid, dim3(128 + 128 * G), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
+    RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L, P>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
                              bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
                              temp_rects, bank.cap, g_dbg, g_dbg_flags));                                                 \
   } while (0)
-  // softmax warpgroups: 2 halve the Q-load / drain phases of an item and the per-tile softmax latency (measured at C3:
-  // strict 88.3 -> 85.9 us, fast 49.8 -> 49.1 us, mixed 58.4 -> 60.2 us, hence 1 there); RMNET_UMMA_NWG=1|2 overrides (A/B)
-  int nwg = (lo && !plo) ? 1 : 2;
-  if (const char *e = getenv("RMNET_UMMA_NWG")) nwg = (e[0] == '2') ? 2 : 1;
-#define RMNET_LAUNCH_UMMA_G(F, L, P) do { if (nwg == 2) RMNET_LAUNCH_UMMA(F, L, P, 2); else RMNET_LAUNCH_UMMA(F, L, P, 1); } while (0)
-  if (fmt == 0 && plo) RMNET_LAUNCH_UMMA_G(0, true, true);
-  else if (fmt == 0 && lo) RMNET_LAUNCH_UMMA_G(0, true, false);
-  else if (fmt == 0) RMNET_LAUNCH_UMMA_G(0, false, false);
-  else if (plo) RMNET_LAUNCH_UMMA_G(1, true, true);
-  else if (lo) RMNET_LAUNCH_UMMA_G(1, true, false);
-  else RMNET_LAUNCH_UMMA_G(1, false, false);
-#undef RMNET_LAUNCH_UMMA_G
+  if (fmt == 0 && plo) RMNET_LAUNCH_UMMA(0, true, true);
+  else if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true, false);
+  else if (fmt == 0) RMNET_LAUNCH_UMMA(0, false, false);
+  else if (plo) RMNET_LAUNCH_UMMA(1, true, true);
+  else if (lo) RMNET_LAUNCH_UMMA(1, true, false);
+  else RMNET_LAUNCH_UMMA(1, false, false);
 #undef RMNET_LAUNCH_UMMA
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
