@@ -201,6 +201,15 @@ RMNET_API int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_
                            int precision, int impl, int stages, float *mem_val, void *workspace,
                            size_t workspace_bytes, void *stream);
 
+/* Host copy of the work plan that the last query-side / pack launch on this workspace built for the tcgen05 read kernel
+ * (introspection and tests; synchronises `stream`).  The plan cuts every object's stored cells into KV chunks of 64-cell
+ * tiles and assigns (object, query tile, Cv half, chunk) pieces to the persistent CTAs:
+ *   ns_out [n_obj]        partial slots (= chunks) per object, <= 16
+ *   hdr_out [256][2]      per CTA: number of pieces, index of its first piece      (n_ctas_out CTAs are in use)
+ *   pieces_out [max_pieces][4]   object | query_tile << 8 | half << 16 | slot << 20,  first tile,  tiles,  stored cells */
+RMNET_API int rmnet_memory_read_plan_host(const void *workspace, int n_obj, int h, int w, int *ns_out, int *hdr_out,
+                                          int *pieces_out, int max_pieces, int *n_ctas_out, void *stream);
+
 /* ---------------------------------------------------------------------------------------------
  * One frame of the reference's loop body in ONE call (models/rmnet.py:414-432 minus the convolutions), batch 1:
  *   rmnet_frame_regions_forward(prev_mask, flow)  ->  rmnet_bank_memorize(k4, v4, mem_rects[1..n])

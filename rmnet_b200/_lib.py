@@ -49,6 +49,7 @@ PROTOTYPES = {
     "rmnet_memory_read_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "rmnet_bank_memory_read": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_int,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "rmnet_memory_read_plan_host": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "rmnet_frame_step": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int,
                                  c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
                                  c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),

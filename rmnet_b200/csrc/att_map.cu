@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 namespace rmnet {
+RMNET_DEV_STAMPS(att_map)
 namespace {
 
 constexpr int kThreads = 256;
@@ -320,6 +321,7 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
   extern __shared__ int s_acc[];  // [2][K][5] CTA accumulators (zero identity, mins inverted): warped, direct
   __shared__ bool s_last;
   pdl_trigger();  // head of the frame-step chain: the successor (bank pack) may start launching; it waits for this grid
+  DEV_STAMP_MIN(0);
   const int b = blockIdx.y;
   // side duty for rmnet_frame_step: zero the bank's temporary-frame value sums (replaces a memset node in the chain)
   if (clear && blockIdx.x == 0 && b == 0) for (int k = threadIdx.x; k < n_clear; k += kThreads) clear[k] = 0.f;
@@ -439,6 +441,7 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
     }
     if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);
   }
+  DEV_STAMP_MAX(1);
 }
 
 // ---- closed-form /16 cell rectangles (models/rmnet.py:245, :307+:356) -----------------------------

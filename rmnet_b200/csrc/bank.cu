@@ -9,6 +9,10 @@
 //   16-bit hi/lo split (x ~= hi + lo) so the read kernel needs no operand conversion stage,
 //   per-channel sum of the stored values (the read of an out-of-region query is sum(V)/M).
 #include "common.cuh"
+namespace rmnet {
+RMNET_DEV_STAMPS(bank)
+}
+#include "sched.cuh"
 
 namespace rmnet {
 namespace {
@@ -21,13 +25,14 @@ constexpr int kGroups = kPackThreads / kCellsPerCta; // 4 channel groups; lanes 
 constexpr int kPerThread = kChunk / kGroups;         // 32 channels per thread
 
 // CTA roles (blockIdx.y + role_base): the memory side of models/rmnet.py:239-248 and the query side of :355-358, :163
-enum { ROLE_MEM_KEYS = 0, ROLE_MEM_VALS = 1 /* ..4 */, ROLE_Q_KEYS = 5, ROLE_Q_PASS = 6 /* ..9 */ };
+enum { ROLE_MEM_KEYS = 0, ROLE_MEM_VALS = 1 /* ..4 */, ROLE_Q_KEYS = 5, ROLE_Q_PASS = 6 /* ..9 */, ROLE_PLAN = 10 /* one CTA: sched.cuh */ };
 
 struct PackSmem {
   __align__(16) uint16_t hi[kCellsPerCta][kKRowStride];
   __align__(16) uint16_t lo[kCellsPerCta][kKRowStride];
   float vsum[kChunk];
 };
+static_assert(sizeof(PlanSmem) <= sizeof(PackSmem), "the plan role reuses the pack CTA's shared memory");
 
 // 64 compact cells x 128 key channels: gather from the channels-first frame -> 16-bit hi/lo split -> transpose through
 // smem -> 256 B position-major rows.  Rows [cnt, rows) are written as zeros.
@@ -85,14 +90,26 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
                  const float *__restrict__ v4, long long v_obj_stride, long long v_ch_stride,
                  const int *__restrict__ rects, QuerySide qs, int role_base, int h, int w) {
   __shared__ PackSmem sm;
+  DEV_STAMP_MIN(2);
   pdl_wait();     // chained launch: the rectangles come from the region kernel right before us
   pdl_trigger();  // (after the wait: the successor's prologue may then rely on everything before this kernel)
+  DEV_STAMP_MIN(3);
   const int o = blockIdx.z;
   const int role = blockIdx.y + role_base;
   const int N = h * w;
 
+  if (role == ROLE_PLAN) {
+    // ---- work plan of the tcgen05 read that follows this launch (one CTA; sched.cuh).  With memory roles in the launch
+    //      the temporary frame's cell counts come from `rects`, exactly as the memory roles below derive them.
+    if (blockIdx.x != 0 || o != 0 || !qs.plan_hdr) return;
+    plan_build(*reinterpret_cast<PlanSmem *>(&sm), qs.plan_bank_meta, qs.q_rects, role_base == ROLE_MEM_KEYS ? rects : nullptr,
+               qs.plan_cap_cells, (int)gridDim.z, h, w, qs.plan_ctas, qs.plan_precision, qs.plan_ns,
+               reinterpret_cast<int2 *>(qs.plan_hdr), reinterpret_cast<int4 *>(qs.plan_pieces), qs.plan_piece_cap);
+    DEV_STAMP_MAX(11);
+    return;
+  }
   if (role >= ROLE_Q_KEYS) {
-    const int4 qrect = qs.q_rects ? __ldg(reinterpret_cast<const int4 *>(qs.q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
+    const int4 qrect = qs.q_rects ? ld_dep(reinterpret_cast<const int4 *>(qs.q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
     if (role == ROLE_Q_KEYS) {
       // ---- query keys (k4e * att16, :357): compact 16-bit planes [o][nq_pad][128] (32-row interleaved, see
       //      pack_key_rows), zero rows up to the next 128
@@ -105,6 +122,7 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
       const bool sat = pack_key_rows<FMT, true>(sm, qs.q_key + (long long)o * qs.q_key_obj_stride, (long long)N, qrect, w, i0,
                                                 max(0, min(kCellsPerCta, r - i0)), kCellsPerCta, qs.qhi + row0, qs.qlo + row0);
       if (sat && qs.range_flag && threadIdx.x == 0) atomicOr(qs.range_flag, 1);
+      DEV_STAMP_MAX(4);
       return;
     }
     // ---- q_val passthrough (v4e * att16 into channels 512..1023 of mem_val, :358 + :163): 64 cells x 128 channels.
@@ -132,6 +150,7 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
         x[k].x *= in_q[0]; x[k].y *= in_q[1]; x[k].z *= in_q[2]; x[k].w *= in_q[3];
         *reinterpret_cast<float4 *>(out + (size_t)(cb + k) * N + pa) = x[k];
       }
+      DEV_STAMP_MAX(4);
     } else {
       const int pos = p_base + (threadIdx.x & (kCellsPerCta - 1));
       if (pos >= N) return;
@@ -143,7 +162,7 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
     return;
   }
 
-  const int4 rect = __ldg(reinterpret_cast<const int4 *>(rects) + o);
+  const int4 rect = ld_dep(reinterpret_cast<const int4 *>(rects) + o);  // (from the region kernel, our predecessor)
   const int r = rect_cells(rect);
   int *meta = bank.meta + o * 8;
   const int base = meta[META_CELLS_C];
@@ -163,6 +182,7 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
     if (pack_key_rows<FMT, false>(sm, k4 + (long long)o * k_obj_stride, k_ch_stride, rect, w, i0, cnt, cnt, bank.khi + row0, bank.klo + row0) &&
         threadIdx.x == 0)
       atomicOr(meta + META_RANGE, 1);
+    DEV_STAMP_MAX(4);
     return;
   }
 
@@ -213,6 +233,7 @@ bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_st
   if (threadIdx.x < kChunk)
     atomicAdd(reinterpret_cast<unsigned long long *>(bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV + cbase + threadIdx.x),
               (unsigned long long)__float2ll_rn(sm.vsum[threadIdx.x] * VSUM_SCALE));
+  DEV_STAMP_MAX(4);
 }
 
 // `keys = this_keys` (models/rmnet.py:424-426): the temporary frame becomes permanent.
@@ -239,7 +260,7 @@ using namespace rmnet;
 // Query side alone (standalone rmnet_bank_memory_read): roles 5..9 of the pack kernel.
 int rmnet::launch_query_side(const QuerySide &qs, int n_obj, int h, int w, int elem_format, cudaStream_t st) {
   BankView none = {};
-  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), 5, n_obj);
+  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), qs.plan_hdr ? 6 : 5, n_obj);
   if (elem_format == 0)
     RMNET_CUDA(launch_kernel(bank_pack_kernel<0>, grid, dim3(kPackThreads), 0, st, false, none, (const float *)nullptr, 0LL, 0LL,
                              (const float *)nullptr, 0LL, 0LL, (const int *)nullptr, qs, (int)ROLE_Q_KEYS, h, w));
@@ -297,7 +318,7 @@ int rmnet::bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int ca
   // with a query side (rmnet_frame_step) the same launch also packs the query keys and writes the q_val passthrough
   QuerySide qs = {};
   if (query_side) qs = *query_side;
-  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), query_side ? 10 : 5, n_obj);
+  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), query_side ? (qs.plan_hdr ? 11 : 10) : 5, n_obj);
   if (elem_format == 0)
     RMNET_CUDA(launch_kernel(bank_pack_kernel<0>, grid, dim3(kPackThreads), 0, st, chained, bv, k4, k_obj_stride, k_ch_stride, v4,
                              v_obj_stride, v_ch_stride, rects, qs, 0, h, w));

@@ -50,6 +50,48 @@ void count_launch(int n = 1);
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+
+// Loads of data that the PREDECESSOR grid of the chain wrote (it may still be running when this grid starts): they must
+// stay behind pdl_wait().  `__ldg` / `const __restrict__` loads are "invariant" to the compiler, which is free to hoist
+// them above the wait's memory clobber once their address is known there -- seen in merge.cu when the address arithmetic
+// moved in front of the wait: the release build read the previous launch's partial results, a build with a time stamp
+// between the wait and the loads did not.  These are volatile asm with a memory clobber (ld.global.cg: L2, no L1 line).
+__device__ __forceinline__ int ld_dep(const int *p) {
+  int v;
+  asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_dep(const float *p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ld_dep(const long long *p) {
+  long long v;
+  asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float2 ld_dep(const float2 *p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int2 ld_dep(const int2 *p) {
+  int2 v;
+  asm volatile("ld.global.cg.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 ld_dep(const int4 *p) {
+  int4 v;
+  asm volatile("ld.global.cg.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ld_dep(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
 bool pdl_enabled();  // runtime.cu: false when the environment sets RMNET_DISABLE_PDL=1 (debugging aid)
 
 template <typename... KArgs, typename... Args>
@@ -69,6 +111,25 @@ static inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim
 }
 #endif
 
+// ---- development aid (`make DEV=1` only): first-start / last-end %globaltimer stamps of the kernels of the frame-step
+//      chain (tools/chain_timeline.py).  In the release build the macros are empty.
+#if defined(RMNET_DEV) && defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long dev_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define RMNET_DEV_STAMPS(tu)                                                  \
+  static __device__ unsigned long long *s_chain_stamps = nullptr;             \
+  void dev_set_chain_stamps_##tu(unsigned long long *p) { cudaMemcpyToSymbol(s_chain_stamps, &p, sizeof(p)); }
+#define DEV_STAMP_MIN(k) do { if (s_chain_stamps && threadIdx.x == 0) atomicMin(s_chain_stamps + (k), dev_globaltimer()); } while (0)
+#define DEV_STAMP_MAX(k) do { if (s_chain_stamps && threadIdx.x == 0) atomicMax(s_chain_stamps + (k), dev_globaltimer()); } while (0)
+#else
+#define RMNET_DEV_STAMPS(tu)
+#define DEV_STAMP_MIN(k) do { } while (0)
+#define DEV_STAMP_MAX(k) do { } while (0)
+#endif
+
 // internal cross-file entry points of the frame-step chain (att_map.cu, bank.cu)
 int frame_regions_chain_head(const float *prev_mask, const float *flow, int B, int K, int H, int W, int sampler,
                              float prob_threshold, int n_pts_threshold, int n_bbox_loose_pixels, int pad_l, int pad_r, int pad_t,
@@ -86,6 +147,10 @@ struct QuerySide {
   int vec4;                                      // 128-bit accesses allowed for q_val / mem_val
   float *mem_val;
   int *range_flag;                               // optional: set to 1 when a query key saturated the fp16 planes (bank meta, slot 0)
+  // work plan of the tcgen05 read that follows (sched.cuh), built by one extra CTA of this launch; plan_hdr == nullptr: none
+  const int *plan_bank_meta;                     // the bank's per-slot counters
+  int *plan_ns, *plan_hdr, *plan_pieces;
+  int plan_piece_cap, plan_ctas, plan_precision, plan_cap_cells;
 };
 int bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *k4, long long k_obj_stride,
                        long long k_ch_stride, const float *v4, long long v_obj_stride, long long v_ch_stride, const int *rects,
@@ -152,14 +217,19 @@ static inline BankView bank_view(void *bank, int n_slots, int cap) {
 
 // ---- split-KV partial-result workspace (see memory_read_*.cu, merge.cu) ---------------------
 // opart [n_splits][n_obj][512][nq_pad] f32 (unnormalised numerators), ml [n_splits][n_obj][2 halves][nq_pad][2] f32
+// The work plan of the persistent tcgen05 kernel (sched.cuh) lives in the workspace too: it is written by the plan role
+// of the pack / query-side launch that precedes the read and consumed by the read kernel (piece lists) and merge.cu (ns).
+enum { READ_MAX_SPLITS = 16, KV_TILE = 64, MAX_TILES_PER_SPLIT = 64, SCHED_MAX_OBJ = 64, UMMA_QT = 128, PLAN_HDR_CTAS = 256 };
 struct ReadWorkspace {
   float *opart, *ml;
-  int *sched;           // [SCHED_MAX_OBJ] partial slots per object, written by the tcgen05 kernel for merge.cu
+  int *sched;           // [SCHED_MAX_OBJ] partial slots per object
+  int *plan_hdr;        // [PLAN_HDR_CTAS][2] (pieces, first piece) of every persistent CTA
+  int *plan_pieces;     // [plan_piece_cap][4]
   uint16_t *qhi, *qlo;  // [n_obj][nq_pad][128] packed query keys (QuerySide)
   int n_splits, nq_pad;
+  size_t plan_piece_cap;
   size_t total;
 };
-enum { READ_MAX_SPLITS = 16, KV_TILE = 64, MAX_TILES_PER_SPLIT = 64 };
 static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_splits) {
   ReadWorkspace W;
   W.nq_pad = cdiv(N, 128) * 128;
@@ -170,7 +240,15 @@ static inline ReadWorkspace read_workspace(void *ws, int n_obj, int N, int n_spl
   W.ml = (float *)((char *)ws + o);
   o = align_up(o + (size_t)W.n_splits * n_obj * 2 * W.nq_pad * 2 * sizeof(float), 1024);
   W.sched = (int *)((char *)ws + o);
-  o = align_up(o + 64 * sizeof(int), 1024);
+  o = align_up(o + SCHED_MAX_OBJ * sizeof(int), 1024);
+  W.plan_hdr = (int *)((char *)ws + o);
+  o = align_up(o + (size_t)PLAN_HDR_CTAS * 2 * sizeof(int), 1024);
+  {  // piece lists: a dealt plan needs G * rounds <= items + G entries, a water-filling plan G * 16 (sched.cuh)
+    const size_t deal = (size_t)READ_MAX_SPLITS * 2 * n_obj * (W.nq_pad / 128) + PLAN_HDR_CTAS, fill = (size_t)PLAN_HDR_CTAS * 16;
+    W.plan_piece_cap = deal > fill ? deal : fill;
+  }
+  W.plan_pieces = (int *)((char *)ws + o);
+  o = align_up(o + W.plan_piece_cap * 4 * sizeof(int), 1024);
   W.qhi = (uint16_t *)((char *)ws + o);
   o = align_up(o + (size_t)n_obj * W.nq_pad * RMNET_CK * sizeof(uint16_t), 1024);
   W.qlo = (uint16_t *)((char *)ws + o);
@@ -248,111 +326,6 @@ __device__ __forceinline__ int rect_pos(const int4 r, int i, int w) {
   int cy = r.z + i / rw, cx = r.x + i % rw;
   return cy * w + cx;
 }
-// ---- work schedule of the persistent tcgen05 kernel (device side, from the actual cell counts) ----------------------
-// item = (object o, KV chunk j of ns(o), Cv half, query tile qt): a balanced 1/ns(o) share of the object's nt(o) KV
-// tiles for 128 compact queries.  Items are ordered (o, j, half, qt) with qt fastest and dealt round-robin to the
-// persistent CTAs, so CTAs that run side by side stream the SAME key/value tiles (one DRAM fetch, L2 hits for the rest).
-// ns(o) = ceil(nt(o) / c); the chunk length c is chosen among max_nt / k, k = 1..READ_MAX_SPLITS, to minimise
-// rounds(c) * c  (rounds = ceil(#items / #CTAs)), subject to the accumulation-chain bound c <= MAX_TILES_PER_SPLIT.
-enum { SCHED_MAX_OBJ = 64, UMMA_QT = 128 };
-struct SchedTable {
-  int nt[SCHED_MAX_OBJ];         // KV tiles of object o
-  int nqt[SCHED_MAX_OBJ];        // query tiles of object o
-  int ns[SCHED_MAX_OBJ];         // KV chunks (= partial slots) of object o
-  int count[SCHED_MAX_OBJ];      // stored cells of object o (committed + temporary frame)
-  int stable[SCHED_MAX_OBJ];     // cells [0, stable) are not being written by a concurrently running pack kernel
-  int ibase[SCHED_MAX_OBJ + 1];  // first item of object o
-};
-// ceil(a / b) for 0 < b, a < 2^20 via one float multiply and a fix-up (a 32-bit integer division costs ~25 instructions)
-__device__ __forceinline__ unsigned ceil_div_small(unsigned a, unsigned b, float rcp_b) {
-  unsigned q = (unsigned)((float)a * rcp_b);
-  q += (q * b < a) ? 1u : 0u;
-  q += (q * b < a) ? 1u : 0u;
-  q -= (q > 0 && (q - 1u) * b >= a) ? 1u : 0u;
-  return q;
-}
-// Called by ONE FULL WARP (all 32 lanes); lane 0 writes the table.  G = number of persistent CTAs.
-// temp_rects != nullptr (rmnet_frame_step without commit): the temporary frame's cell count is derived from its cell
-// rectangle exactly as bank_pack_kernel derives it, so the table can be built BEFORE the pack kernel has finished
-// (the committed counters do not change during such a step).
-__device__ __forceinline__ void sched_build(SchedTable &T, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
-                                            const int *__restrict__ temp_rects, int cap, int n_obj, int h, int w, int G) {
-  const int lane = threadIdx.x & 31;
-  // per-object tile counts (lanes over objects), also kept in registers for the candidate evaluation
-  int max_nt = 0;
-  for (int o0 = 0; o0 < n_obj; o0 += 32) {
-    const int o = o0 + lane;
-    int nt = 0, nqt = 0;
-    if (o < n_obj) {
-      const int4 qr = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-      int count;
-      if (temp_rects) {
-        const int base = bank_meta[o * 8 + META_CELLS_C];
-        const int r = rect_cells(__ldg(reinterpret_cast<const int4 *>(temp_rects) + o));
-        count = base + (base + r > cap ? 0 : r);  // bank_pack_kernel drops a frame that would overflow the bank
-        T.stable[o] = base;
-      } else {
-        count = bank_meta[o * 8 + META_CELLS_C] + bank_meta[o * 8 + META_CELLS_T];
-        T.stable[o] = count;
-      }
-      nt = (count + KV_TILE - 1) / KV_TILE;
-      nqt = (rect_cells(qr) + UMMA_QT - 1) / UMMA_QT;
-      T.nt[o] = nt;
-      T.nqt[o] = nqt;
-      T.count[o] = count;
-    }
-    max_nt = max(max_nt, __reduce_max_sync(0xffffffffu, nqt > 0 ? nt : 0));
-  }
-  __syncwarp();
-  // candidates: every chunk length c in [c_min, 64] (two per lane), c_min from the partial-slot bound.
-  // 32-bit unsigned arithmetic only: 64-bit integer division is emulated with hundreds of instructions.
-  const unsigned c_min = max(1u, ((unsigned)max_nt + READ_MAX_SPLITS - 1) / READ_MAX_SPLITS);
-  // Both candidates of a lane are evaluated in ONE walk over the objects (independent chains: the walk is latency-
-  // bound integer arithmetic, and in a stand-alone launch it sits on the kernel's critical path).
-  const unsigned cand[2] = {(unsigned)lane + 1u, (unsigned)lane + 33u};
-  const float rcp[2] = {__frcp_rn((float)cand[0]), __frcp_rn((float)cand[1])};
-  unsigned items[2] = {0u, 0u}, longest[2] = {0u, 0u};
-#pragma unroll 2
-  for (int o = 0; o < n_obj; ++o) {
-    const unsigned nt = T.nt[o], w2 = 2u * (unsigned)T.nqt[o];
-    if (nt > 0 && w2 > 0) {
-#pragma unroll
-      for (int rep = 0; rep < 2; ++rep) {
-        const unsigned ns = ceil_div_small(nt, cand[rep], rcp[rep]);
-        items[rep] += ns * w2;
-        longest[rep] = max(longest[rep], ceil_div_small(nt, ns, __frcp_rn((float)ns)));  // balanced chunks: the longest actual chunk
-      }
-    }
-  }
-  unsigned best = 0xffffffffu, best_c = c_min;
-#pragma unroll
-  for (int rep = 0; rep < 2; ++rep) {
-    const unsigned c = cand[rep];
-    if (c >= c_min && c <= MAX_TILES_PER_SPLIT && c <= (unsigned)max(max_nt, 1)) {
-      const unsigned rounds = (items[rep] + G - 1) / (unsigned)G;
-      // makespan estimate in tile units: rounds x (longest chunk + per-item prologue/epilogue ~ 5 tiles); ties -> fewer chunks
-      const unsigned cost = (rounds * (longest[rep] + 5u)) * 128u + (64u - c);
-      if (cost < best) { best = cost; best_c = c; }
-    }
-  }
-  const unsigned bcast = __reduce_min_sync(0xffffffffu, best);
-  const unsigned who = __ballot_sync(0xffffffffu, best == bcast);
-  int c = (int)__shfl_sync(0xffffffffu, best_c, __ffs(who) - 1);
-  if (max_nt > MAX_TILES_PER_SPLIT * READ_MAX_SPLITS) c = (int)c_min;  // huge banks: the slot bound wins over the chain bound
-  if (lane == 0) {
-    int acc = 0;
-    for (int o = 0; o < n_obj; ++o) {
-      const int nt = T.nt[o];
-      const int ns = (nt > 0 && T.nqt[o] > 0) ? (nt + c - 1) / c : 0;
-      T.ns[o] = ns;
-      T.ibase[o] = acc;
-      acc += ns * 2 * T.nqt[o];
-    }
-    T.ibase[n_obj] = acc;
-  }
-  __syncwarp();
-}
-
 // device-side resolution of the split -> [tile_begin, tile_begin + n_it) for `count` stored cells
 __device__ __forceinline__ void split_range(int count, int n_splits, int split, int &tile_begin, int &n_it) {
   const int n_tiles = (count + KV_TILE - 1) / KV_TILE;

@@ -5,10 +5,11 @@ namespace rmnet {
 int launch_memory_read_simt(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st);
-int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int fmt, int precision,
-                            int n_splits, const ReadWorkspace &W, const int *temp_rects, bool pdl, cudaStream_t st);
+int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, const int *q_rects,
+                            int h, int w, float *mem_val, bool pdl, cudaStream_t st);
+int umma_grid_size();
 int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
-                 const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st);
+                 const ReadWorkspace &W, float *mem_val, bool fill_uniform, bool pdl, cudaStream_t st);
 bool umma_supported(int cap_cells);
 int launch_attention_probs(const float *m_key, const float *q_key, int n, int M, int N, float *p, cudaStream_t st);
 
@@ -19,9 +20,21 @@ __global__ void fill_dense_rects_kernel(int *rects, int n, int h, int w) {
 }
 
 
+// plan = true: the launch that prepares the query side also builds the work plan of the tcgen05 read (sched.cuh)
 QuerySide make_query_side(const float *q_key, const float *q_val, long long q_key_obj_stride, const int *q_rects,
-                          const ReadWorkspace &W, int N, float *mem_val, int *range_flag) {
-  QuerySide qs;
+                          const ReadWorkspace &W, int N, float *mem_val, int *range_flag, bool plan, const BankView &bv,
+                          int precision) {
+  QuerySide qs = {};
+  if (plan) {
+    qs.plan_bank_meta = bv.meta;
+    qs.plan_ns = W.sched;
+    qs.plan_hdr = W.plan_hdr;
+    qs.plan_pieces = W.plan_pieces;
+    qs.plan_piece_cap = (int)W.plan_piece_cap;
+    qs.plan_ctas = umma_grid_size();
+    qs.plan_precision = precision;
+    qs.plan_cap_cells = bv.cap;
+  }
   qs.range_flag = range_flag;
   qs.q_key = q_key;
   qs.q_val = q_val;
@@ -37,11 +50,10 @@ QuerySide make_query_side(const float *q_key, const float *q_val, long long q_ke
 }
 
 // chained = true: called from rmnet_frame_step, the launches are programmatic dependents of the pack / commit kernel.
-// temp_rects (optional, chained only): the cell rectangles the pack kernel is storing as the temporary frame.
 int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
                           const float *q_val, long long q_obj_stride, const int *q_rects, int n_obj, int h, int w,
                           int elem_format, int precision, int impl, int stages, float *mem_val, void *workspace,
-                          size_t workspace_bytes, const int *temp_rects, bool chained, void *stream) {
+                          size_t workspace_bytes, bool chained, void *stream) {
   RMNET_CHECK_ARG(bank && q_key && q_val && mem_val && workspace, "null pointer argument");
   RMNET_CHECK_ARG(n_obj > 0 && n_obj <= n_slots && h > 0 && w > 0, "bad shape");
   RMNET_CHECK_ARG(n_obj <= 65535, "too many objects");
@@ -61,17 +73,28 @@ int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int 
   int rc = RMNET_OK;
   const bool umma = impl == RMNET_IMPL_UMMA;
   if (stages & RMNET_STAGE_QUERY) {  // (rmnet_frame_step folds this into its pack launch instead)
-    QuerySide qs = make_query_side(q_key, q_val, q_obj_stride, q_rects, W, h * w, mem_val, bv.meta + META_RANGE);
+    QuerySide qs = make_query_side(q_key, q_val, q_obj_stride, q_rects, W, h * w, mem_val, bv.meta + META_RANGE, umma, bv, precision);
     if ((rc = launch_query_side(qs, n_obj, h, w, elem_format, st))) return rc;
   }
   if (!(stages & RMNET_STAGE_PARTIAL)) {
   } else if (umma)
-    rc = launch_memory_read_umma(bv, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, temp_rects, chained, st);
+#ifdef RMNET_EXP_NO_BGFILL
+    rc = launch_memory_read_umma(bv, n_obj, elem_format, precision, W, q_rects, h, w, nullptr, chained, st);
+#else
+    rc = launch_memory_read_umma(bv, n_obj, elem_format, precision, W, q_rects, h, w, mem_val, chained, st);
+#endif
   else
     rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
   if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
   // the merge is a programmatic dependent of the tcgen05 kernel whenever both run in this call
-  return launch_merge(bv, q_rects, n_obj, h, w, n_splits, umma, W, mem_val, umma && (stages & RMNET_STAGE_PARTIAL), st);
+  // (the tcgen05 kernel writes the uniform rows of mem_val itself; the FFMA path leaves them to the merge kernel)
+  return launch_merge(bv, q_rects, n_obj, h, w, n_splits, umma, W, mem_val, /*fill_uniform=*/
+#ifdef RMNET_EXP_NO_BGFILL
+                      true,
+#else
+                      !umma,
+#endif
+                      umma && (stages & RMNET_STAGE_PARTIAL), st);
 }
 
 }  // namespace
@@ -92,7 +115,23 @@ int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int
                            int elem_format, int precision, int impl, int stages, float *mem_val, void *workspace,
                            size_t workspace_bytes, void *stream) {
   return bank_memory_read_impl(bank, bank_bytes, n_slots, cap_cells, q_key, q_val, q_obj_stride, q_rects, n_obj, h, w, elem_format,
-                               precision, impl, stages, mem_val, workspace, workspace_bytes, nullptr, false, stream);
+                               precision, impl, stages, mem_val, workspace, workspace_bytes, false, stream);
+}
+
+int rmnet_memory_read_plan_host(const void *workspace, int n_obj, int h, int w, int *ns_out, int *hdr_out, int *pieces_out,
+                                int max_pieces, int *n_ctas_out, void *stream) {
+  RMNET_CHECK_ARG(workspace && ns_out && hdr_out && pieces_out && n_ctas_out, "null pointer argument");
+  RMNET_CHECK_ARG(n_obj > 0 && n_obj <= SCHED_MAX_OBJ && h > 0 && w > 0 && max_pieces > 0, "bad argument");
+  ReadWorkspace W = rmnet::read_workspace(const_cast<void *>(workspace), n_obj, h * w, READ_MAX_SPLITS);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = umma_grid_size();
+  const size_t n_pieces = W.plan_piece_cap < (size_t)max_pieces ? W.plan_piece_cap : (size_t)max_pieces;
+  RMNET_CUDA(cudaMemcpyAsync(ns_out, W.sched, (size_t)n_obj * sizeof(int), cudaMemcpyDeviceToHost, st));
+  RMNET_CUDA(cudaMemcpyAsync(hdr_out, W.plan_hdr, (size_t)G * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  RMNET_CUDA(cudaMemcpyAsync(pieces_out, W.plan_pieces, n_pieces * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  RMNET_CUDA(cudaStreamSynchronize(st));
+  *n_ctas_out = G;
+  return RMNET_OK;
 }
 
 int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *prev_mask, const float *flow,
@@ -122,14 +161,13 @@ int rmnet_frame_step(void *bank, size_t bank_bytes, int n_slots, int cap_cells, 
   ReadWorkspace RW = rmnet::read_workspace(read_workspace, n_obj, (int)N, umma ? READ_MAX_SPLITS : pick_splits(n_obj, (int)N, 64, cap_cells));
   if (read_workspace_bytes < RW.total) { set_error("workspace too small: %zu < %zu", read_workspace_bytes, RW.total); return RMNET_E_WORKSPACE; }
   // the pack launch also prepares the query side (packed query keys, q_val passthrough) of this frame's read
-  QuerySide qs = make_query_side(q_key, q_val, 0, cur_rc + 4, RW, (int)N, mem_val, bv.meta + META_RANGE);
+  QuerySide qs = make_query_side(q_key, q_val, 0, cur_rc + 4, RW, (int)N, mem_val, bv.meta + META_RANGE, umma, bv, precision);
   rc = bank_memorize_impl(bank, bank_bytes, n_slots, cap_cells, k4, RMNET_CK * N, N, v4, RMNET_CV * N, N, mem_rc + 4, n_obj, h, w,
                           elem_format, commit, /*chained=*/true, &qs, stream);
   if (rc) return rc;
-  // without a commit the committed counters are stable, so the read kernel can build its schedule before the pack finishes
   return bank_memory_read_impl(bank, bank_bytes, n_slots, cap_cells, q_key, q_val, 0, cur_rc + 4, n_obj, h, w, elem_format,
                                precision, impl, RMNET_STAGE_PARTIAL | RMNET_STAGE_MERGE, mem_val, read_workspace,
-                               read_workspace_bytes, commit ? nullptr : mem_rc + 4, /*chained=*/true, stream);
+                               read_workspace_bytes, /*chained=*/true, stream);
 }
 
 static size_t reader_scratch_layout(int n, int T, int h, int w, size_t *off_rects, size_t *off_read, int *cap) {

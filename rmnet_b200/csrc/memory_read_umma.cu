@@ -20,6 +20,10 @@
 #include <cuda.h>
 
 #include "common.cuh"
+namespace rmnet {
+RMNET_DEV_STAMPS(umma)
+}
+#include "sched.cuh"
 
 namespace rmnet {
 namespace {
@@ -43,6 +47,11 @@ constexpr uint32_t SMEM_BYTES = SMEM_TILES + 1024 /*align slack*/ + 256 /*barrie
 constexpr uint32_t TM_O = 0, TM_S0 = 256, TM_Q_HI = 384, TM_Q_LO = 448;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -164,32 +173,129 @@ struct Barriers {
 };
 
 struct Piece {
-  int o, qtile, half, tile_begin, n_it, slot;
+  int o, qtile, half, tile_begin, n_it, slot, count;
 };
-// Enumerates the work items of persistent CTA `cta` (items cta, cta + n_ctas, ...); every warp role walks the same sequence.
+// The pieces of this CTA in execution order (the plan of sched.cuh, written by the launch before this one); every warp
+// role walks the same list.  The first PLAN_SMEM_PIECES entries are staged in shared memory.
 struct PieceIter {
-  const SchedTable *T;
-  int n_obj, item, stride;
-  __device__ PieceIter(const SchedTable *t, int n_obj_, int cta, int n_ctas) : T(t), n_obj(n_obj_), item(cta - n_ctas), stride(n_ctas) {}
+  const int4 *cached, *all;
+  int n, k;
+  __device__ PieceIter(const int4 *cached_, const int4 *all_, int n_) : cached(cached_), all(all_), n(n_), k(0) {}
   __device__ bool next(Piece &p) {
-    item += stride;
-    if (item >= T->ibase[n_obj]) return false;
-    int o = 0;
-    while (T->ibase[o + 1] <= item) ++o;  // objects without work own no items and are skipped
-    unsigned r = (unsigned)(item - T->ibase[o]);
-    const unsigned nqt = T->nqt[o], nt = T->nt[o], ns = T->ns[o];
-    p.o = o;
-    const unsigned q = r / nqt;       // 32-bit unsigned divisions only (64-bit ones cost hundreds of instructions)
-    p.qtile = (int)(r - q * nqt);
-    p.half = (int)(q & 1u);
-    const unsigned j = q >> 1;
-    p.slot = (int)j;
-    const unsigned t0 = (j * nt) / ns, t1 = ((j + 1u) * nt) / ns;  // balanced partition of the nt tiles into ns chunks
-    p.tile_begin = (int)t0;
-    p.n_it = (int)(t1 - t0);
+    if (k >= n) return false;
+    const int4 v = k < PLAN_SMEM_PIECES ? cached[k] : ld_dep(all + k);
+    ++k;
+    p.o = v.x & 255;
+    p.qtile = (v.x >> 8) & 255;
+    p.half = (v.x >> 16) & 15;
+    p.slot = (int)((unsigned)v.x >> 20);
+    p.tile_begin = v.y;
+    p.n_it = v.z;
+    p.count = v.w;
     return true;
   }
 };
+
+// Uniform rows of mem_val (an out-of-region query reads sum(V) / M, merge.cu's header), written in the background by the
+// otherwise idle warp 3 of every CTA while the tensor pipe works: 12.6 MB of stores at the headline size that the merge
+// kernel used to issue after the read (its CTAs cannot start earlier: every SM is busy with a read CTA until the end).
+struct UniformFill {
+  const long long *vsum;  // BankView::vsum
+  const int *meta;        // BankView::meta
+  const int *q_rects;     // [n_obj][4] or nullptr (dense: nothing to fill)
+  float *mem_val;         // nullptr = no fill
+  int h, w, n_slots, vec4;
+};
+// One warp; a single warp issues a dependent instruction every ~5 cycles, so the instruction count per stored byte is what
+// matters here.  CTA `cta` owns a CONTIGUOUS block of rows (object, channel) -- at most two objects -- taken 32 at a time:
+// lane r fetches the value of row r of the batch (one round trip for the batch), then the warp stores row after row.  Per
+// object the lane's "cell is inside the query rectangle" bits are computed once (4 bits per 128-cell step of the row, up
+// to 32 steps = 4 096 cells in two 64-bit registers), so a row costs ~5 instructions per 512-byte store.
+__device__ __forceinline__ void fill_uniform_rows(const UniformFill &f, int cta, int n_ctas, int n_obj) {
+  if (!f.mem_val || !f.q_rects) return;
+  const int lane = threadIdx.x & 31;
+  const int N = f.h * f.w;
+  const int n_rows = n_obj * RMNET_CV;
+  const int per_cta = (n_rows + n_ctas - 1) / n_ctas;
+  const int row_end = min(n_rows, (cta + 1) * per_cta);
+  const int n_steps = (N + 127) / 128;
+  const bool fast = f.vec4 && n_steps <= 32;
+  int cur_o = -1;
+  int4 qr = make_int4(0, 0, 0, 0);
+  bool skip = true;
+  unsigned long long in_lo = 0ull, in_hi = 0ull;
+  for (int r0 = cta * per_cta; r0 < row_end; r0 += 32) {
+    float my_u = 0.f;
+    if (r0 + lane < row_end) {
+      const int row = r0 + lane;
+      const int o = row / RMNET_CV, ch = row - o * RMNET_CV;
+      const int *meta = f.meta + o * 8;
+      const int M = ld_dep(meta + META_ZEROS_C) + ld_dep(meta + META_ZEROS_T) + ld_dep(meta + META_CELLS_C) + ld_dep(meta + META_CELLS_T);
+      const long long *vs_c = f.vsum + (size_t)o * RMNET_CV, *vs_t = f.vsum + ((size_t)f.n_slots + o) * RMNET_CV;
+      my_u = (__ll2float_rn(ld_dep(vs_c + ch) + ld_dep(vs_t + ch)) * VSUM_INV_SCALE) * (1.0f / (float)M);  // merge.cu's expression
+    }
+    const int nb = min(32, row_end - r0);
+    for (int j = 0; j < nb; ++j) {
+      const int row = r0 + j;
+      const float u = __shfl_sync(0xffffffffu, my_u, j);
+      const int o = row / RMNET_CV, ch = row - o * RMNET_CV;
+      if (o != cur_o) {
+        cur_o = o;
+        qr = __ldg(reinterpret_cast<const int4 *>(f.q_rects) + o);
+        skip = rect_cells(qr) == N;
+        if (fast && !skip) {
+          in_lo = in_hi = 0ull;
+          const int p0 = lane * 4;
+          int cy = p0 / f.w, cx = p0 - cy * f.w;          // the lane's quad of step 0; every step advances it by 128 cells
+          const int dy = 128 / f.w, dx = 128 - dy * f.w;
+          for (int it = 0; it < n_steps; ++it) {
+            unsigned m = 15u;  // cells beyond N count as "inside": never stored
+            if (it * 128 + p0 < N) {
+              int ey = cy, ex = cx;
+              m = 0u;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (ex >= qr.x && ex <= qr.y && ey >= qr.z && ey <= qr.w) m |= 1u << e;
+                if (++ex == f.w) { ex = 0; ++ey; }
+              }
+            }
+            if (it < 16) in_lo |= (unsigned long long)m << (4 * it);
+            else in_hi |= (unsigned long long)m << (4 * (it - 16));
+            cy += dy; cx += dx;
+            if (cx >= f.w) { cx -= f.w; ++cy; }
+          }
+        }
+      }
+      if (skip) continue;
+      float *out = f.mem_val + ((size_t)o * 2 * RMNET_CV + ch) * N + lane * 4;
+      if (fast) {
+        unsigned long long bits = in_lo;
+#pragma unroll 1
+        for (int it0 = 0; it0 < n_steps; it0 += 16, bits = in_hi) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (it0 + i < n_steps) {
+              const unsigned m = (unsigned)(bits >> (4 * i)) & 15u;
+              float *q = out + (it0 + i) * 128;
+              if (m == 0u) {
+                *reinterpret_cast<float4 *>(q) = make_float4(u, u, u, u);
+              } else if (m != 15u) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) if (!((m >> e) & 1u)) q[e] = u;
+              }
+            }
+          }
+        }
+      } else {
+        out -= lane * 4;
+        for (int p = lane; p < N; p += 32) {
+          const int cy = p / f.w, cx = p - cy * f.w;
+          if (!(cx >= qr.x && cx <= qr.y && cy >= qr.z && cy <= qr.w)) out[p] = u;
+        }
+      }
+    }
+  }
+}
 
 // USE_LO: the score product Q.K^T takes the 3-term hi/lo split (K lo plane loaded, Q lo plane in TMEM);
 // PV_LO : so does the P.V product (V lo plane loaded, P split into hi/lo).  (true, true) = strict, (false, false) = fast,
@@ -198,10 +304,10 @@ template <int FMT, bool USE_LO, bool PV_LO>
 __global__ void __launch_bounds__(kThreads, 1)
 memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __grid_constant__ CUtensorMap map_klo,
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
-                        const int *__restrict__ bank_meta, const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
-                        const int *__restrict__ q_rects, int h, int w,
-                        float *__restrict__ opart, float *__restrict__ ml, int *__restrict__ sched_out, int nq_pad,
-                        int n_obj, const int *__restrict__ temp_rects, int cap, float *__restrict__ dbg_arg, int dbg_flags_arg) {
+                        const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
+                        const int2 *__restrict__ plan_hdr, const int4 *__restrict__ plan_pieces,
+                        float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj, const UniformFill fill,
+                        float *__restrict__ dbg_arg, int dbg_flags_arg) {
   // Development instrumentation (S dump, clock64 stamps, the no-TMA experiment) exists only in -DRMNET_DEV builds
   // (`make DEV=1`); in the release build the hooks are compile-time nulls and every branch on them is dead code.
 #ifdef RMNET_DEV
@@ -212,29 +318,29 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   constexpr int dbg_flags = 0;
   (void)dbg_arg; (void)dbg_flags_arg;
 #endif
+  DEV_STAMP_MIN(5);
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char *smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
   Barriers *bars = reinterpret_cast<Barriers *>(smem_al + SMEM_TILES);
   const uint32_t k_smem = smem_base, v_smem = smem_base + KST * K_STAGE_BYTES;
-  __shared__ SchedTable sched;
+  __shared__ int4 s_pieces[PLAN_SMEM_PIECES];
+  __shared__ int2 s_hdr;
 
 #ifdef RMNET_DEV
-  long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 16 : nullptr;
+  long long *tstamp = dbg ? reinterpret_cast<long long *>(dbg + 8448) + (size_t)blockIdx.x * 32 : nullptr;
 #else
   constexpr long long *tstamp = nullptr;
 #endif
-  if (tstamp && threadIdx.x == 128) tstamp[0] = clock64();
+  if (tstamp && threadIdx.x == 128) { tstamp[0] = clock64(); tstamp[16] = (long long)globaltimer_ns(); }
   constexpr int fmt = FMT;
   constexpr bool use_lo = USE_LO;
   constexpr bool pv_lo = PV_LO;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  // ---- one-time setup, three warps in parallel: schedule (warp 3), barriers (warp 0), TMEM (warp 1).
-  //      Chained launch (PDL): everything up to pdl_wait() overlaps the tail of the pack kernel.
+  // ---- one-time setup: barriers (warp 0) and TMEM (warp 1) before the dependency wait -- in a chained launch (PDL)
+  //      this overlaps the tail of the pack kernel -- then the CTA's piece list (warp 3).
   if (tstamp && threadIdx.x == 96) tstamp[8] = clock64();
-  if (warp == 3 && temp_rects) sched_build(sched, bank_meta, q_rects, temp_rects, cap, n_obj, h, w, (int)gridDim.x);
-  if (tstamp && threadIdx.x == 32) tstamp[10] = clock64();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_khi); tma_prefetch_desc(&map_klo); tma_prefetch_desc(&map_vhi); tma_prefetch_desc(&map_vlo);
     for (int i = 0; i < KST; ++i) { mbar_init(smem_u32(&bars->k_full[i]), 1); mbar_init(smem_u32(&bars->k_empty[i]), 1); }
@@ -252,26 +358,24 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tstamp && threadIdx.x == 32) tstamp[11] = clock64();
-  // Chained launch with an early schedule (temp_rects): only the threads that touch the pack kernel's output wait --
-  // the TMA producers right before their first tile that reaches into the temporary frame, the softmax warpgroup before
-  // it reads the packed query keys; tiles of the committed frames stream in while the pack kernel is still running.
-  // Otherwise (standalone launch, or a commit in the chain) everybody waits here and the schedule is built afterwards.
-  const bool early = temp_rects != nullptr;
-  if (!early) {
-    pdl_wait();
-    if (warp == 3) sched_build(sched, bank_meta, q_rects, nullptr, cap, n_obj, h, w, (int)gridDim.x);
+  pdl_wait();  // the plan, the packed queries and the temporary frame all come from the launch before this one
+  if (warp == 3) {
+    const int2 hd = ld_dep(plan_hdr + blockIdx.x);  // (everything the pack kernel wrote: ld_dep, common.cuh)
+    if (lane == 0) s_hdr = hd;
+    for (int k = lane; k < min(hd.x, (int)PLAN_SMEM_PIECES); k += 32) s_pieces[k] = ld_dep(plan_pieces + hd.y + k);
   }
   if (tstamp && threadIdx.x == 96) tstamp[9] = clock64();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (blockIdx.x == 0 && threadIdx.x < n_obj) sched_out[threadIdx.x] = sched.ns[threadIdx.x];  // for merge.cu
-  if ((int)blockIdx.x >= sched.ibase[n_obj]) {  // no work for this CTA (uniform): give the TMEM back and leave
+  if (s_hdr.x == 0) {  // no pieces for this CTA (uniform): give the TMEM back, do the CTA's share of the uniform rows, leave
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(bars->tmem_base), "r"(512u) : "memory");
+    if (warp == 4) pdl_trigger();
+    if (warp == 3) fill_uniform_rows(fill, (int)blockIdx.x, (int)gridDim.x, n_obj);
     return;
   }
   const uint32_t tmem = bars->tmem_base;
-  PieceIter iter(&sched, n_obj, (int)blockIdx.x, (int)gridDim.x);
+  PieceIter iter(s_pieces, plan_pieces + s_hdr.y, s_hdr.x);
   Piece pc;
   if (tstamp && threadIdx.x == 128) tstamp[1] = clock64();
 
@@ -279,11 +383,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     // ================= key-tile TMA producer =================
     if (lane == 0) {
       int kt = 0;  // key tiles issued by this CTA so far (ring position / parity run across pieces)
-      bool waited = !early;
       while (iter.next(pc)) {
         for (int it = 0; it < pc.n_it; ++it, ++kt) {
           const int s = kt % KST;
-          if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->k_empty[s]), ((kt / KST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->k_full[s]);
           if ((dbg_flags & 1) && kt >= KST) { mbar_arrive(full); continue; }  // dev experiment: no TMA traffic after the ring fill (results are garbage)
@@ -303,11 +405,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     // ================= value-tile TMA producer =================
     if (lane == 0) {
       int vt = 0;
-      bool waited = !early;
       while (iter.next(pc)) {
         for (int it = 0; it < pc.n_it; ++it, ++vt) {
           const int s = vt % VST;
-          if (!waited && (pc.tile_begin + it + 1) * MT > sched.stable[pc.o]) { pdl_wait(); waited = true; }
           mbar_wait(smem_u32(&bars->v_empty[s]), ((vt / VST) & 1) ^ 1);
           const uint32_t full = smem_u32(&bars->v_full[s]);
           if ((dbg_flags & 1) && vt >= VST) { mbar_arrive(full); continue; }
@@ -386,6 +486,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         if (st < pc.n_it) issue_qk();
       }
     }
+  } else if (warp == 3) {
+    // ================= background: the uniform rows of mem_val =================
+    fill_uniform_rows(fill, (int)blockIdx.x, (int)gridDim.x, n_obj);
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue warpgroup: thread <-> query row <-> TMEM lane =================
     const int row = threadIdx.x - 128;                  // 0..127
@@ -394,8 +497,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     const float scale = 1.4426950408889634f * rsqrtf((float)RMNET_CK);
     int gt = 0;  // global tile counter (S/P buffer + barrier parity), runs across pieces
     bool first_piece = true;
-    if (early) pdl_wait();  // the packed query keys (and, through the barriers, everything downstream) need the pack kernel
-    pdl_trigger();          // after the wait: the merge kernel's pre-wait part relies on the bank being final
+    pdl_trigger();  // (after the wait above: the merge kernel's pre-wait part relies on the bank being final)
     // this row's 128 query-key channels as packed 16-bit pairs (hi and lo planes), written by the pack kernel's
     // query role in the TMEM column order (column c = channels 2c, 2c+1), 32 rows interleaved per 16 B chunk so that
     // each of the loads below is one coalesced 512 B access per warp
@@ -405,13 +507,13 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r, *pl = reinterpret_cast<const uint4 *>(qlo) + r;
 #pragma unroll
       for (int j = 0; j < RMNET_CK / 8; ++j) {
-        const uint4 v = __ldg(ph + j * 32);
+        const uint4 v = ld_dep(ph + j * 32);
         qh[4 * j] = v.x; qh[4 * j + 1] = v.y; qh[4 * j + 2] = v.z; qh[4 * j + 3] = v.w;
       }
       if (USE_LO) {
 #pragma unroll
         for (int j = 0; j < RMNET_CK / 8; ++j) {
-          const uint4 v = __ldg(pl + j * 32);
+          const uint4 v = ld_dep(pl + j * 32);
           ql[4 * j] = v.x; ql[4 * j + 1] = v.y; ql[4 * j + 2] = v.z; ql[4 * j + 3] = v.w;
         }
       }
@@ -439,7 +541,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(smem_u32(&bars->q_ready));
-        if (tstamp && first_piece && row == 0) tstamp[2] = clock64();
+        if (tstamp && first_piece && row == 0) { tstamp[2] = clock64(); tstamp[21] = (long long)globaltimer_ns(); }
       }
       if (have_cur) {
         // ---- epilogue of the current piece: unnormalised numerators for merge.cu, partial slot pc.slot
@@ -475,7 +577,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       have_cur = true;
       const int o = pc.o;
       const int n = pc.qtile * QT + row;
-      const int count = sched.count[o];
+      const int count = pc.count;
 
       float m_ref = -INFINITY, l_sum = 0.f;
       for (int it = 0; it < pc.n_it; ++it, ++gt) {
@@ -566,7 +668,9 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
       if (dbg && first_piece && blockIdx.x == 0) dbg[QT * MT + row] = m_ref;
       if (tstamp && first_piece && row == 0) { tstamp[4] = clock64(); tstamp[7] = pc.n_it; }
       have_nxt = iter.next(nxt);
+      if (tstamp && row == 0) { tstamp[19] += 1; tstamp[22] += pc.n_it; if (tstamp[19] == 1) tstamp[18] = pc.o | (pc.qtile << 8) | (pc.half << 16) | (pc.slot << 20); }
     }
+    if (tstamp && row == 0) { tstamp[20] = clock64(); tstamp[17] = (long long)globaltimer_ns(); }
   }
 
   // ---- teardown
@@ -575,6 +679,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+  DEV_STAMP_MAX(6);
 }
 
 // ---- host: TMA descriptors ------------------------------------------------------------------------
@@ -626,8 +731,12 @@ int umma_grid_size() {
   return n_sms;
 }
 
-int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int fmt, int precision,
-                            int n_splits, const ReadWorkspace &W, const int *temp_rects, bool pdl, cudaStream_t st) {
+// The work plan (W.plan_hdr / W.plan_pieces / W.sched) must have been written by the launch right before this one in the
+// stream: the pack kernel of rmnet_frame_step or the query-side launch of rmnet_bank_memory_read (bank.cu: ROLE_PLAN).
+// q_rects / h / w / mem_val: for the uniform rows of mem_val (cells outside an object's query rectangle), which the kernel
+// writes in the background; mem_val == nullptr skips them.
+int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, const int *q_rects,
+                            int h, int w, float *mem_val, bool pdl, cudaStream_t st) {
   RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
   RMNET_CHECK_ARG(n_obj <= SCHED_MAX_OBJ, "tcgen05 path supports at most %d objects per call", (int)SCHED_MAX_OBJ);
   // The four tensor maps depend only on the bank (base pointers, capacity, slots): encode once per bank and thread.
@@ -654,8 +763,12 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
   const CUtensorMap &mkh = mc->m[0], &mkl = mc->m[1], &mvh = mc->m[2], &mvl = mc->m[3];
   const int n_sms = umma_grid_size();
   dim3 grid(n_sms);
-  (void)n_splits;
+  RMNET_CHECK_ARG(n_sms <= PLAN_HDR_CTAS && W.nq_pad / 128 <= 256, "tcgen05 path: %d SMs / %d query tiles exceed the plan's limits", n_sms, W.nq_pad / 128);
   const bool lo = precision != RMNET_PREC_SINGLE, plo = precision == RMNET_PREC_SPLIT3;
+  UniformFill fill;
+  fill.vsum = bank.vsum; fill.meta = bank.meta; fill.q_rects = q_rects; fill.mem_val = mem_val;
+  fill.h = h; fill.w = w; fill.n_slots = bank.n_slots;
+  fill.vec4 = ((h * w) % 4 == 0 && (uintptr_t)mem_val % 16 == 0) ? 1 : 0;
 #define RMNET_LAUNCH_UMMA(F, L, P)                                                                                          \
   do {                                                                                                                   \
     static bool attr_set[64] = {};                                                                                       \
@@ -667,8 +780,9 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
       if (dev_ >= 0 && dev_ < 64) attr_set[dev_] = true;                                                                 \
     }                                                                                                                    \
     RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L, P>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
-                             bank.meta, W.qhi, W.qlo, q_rects, h, w, W.opart, W.ml, W.sched, W.nq_pad, n_obj,           \
-                             temp_rects, bank.cap, g_dbg, g_dbg_flags));                                                 \
+                             W.qhi, W.qlo, reinterpret_cast<const int2 *>(W.plan_hdr),                                  \
+                             reinterpret_cast<const int4 *>(W.plan_pieces), W.opart, W.ml, W.nq_pad, n_obj, fill, g_dbg,\
+                             g_dbg_flags));                                                                              \
   } while (0)
   if (fmt == 0 && plo) RMNET_LAUNCH_UMMA(0, true, true);
   else if (fmt == 0 && lo) RMNET_LAUNCH_UMMA(0, true, false);
@@ -689,4 +803,13 @@ int launch_memory_read_umma(const BankView &bank, const int *q_rects, int n_obj,
 extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_dump(float *ptr) { rmnet::g_dbg = ptr; }
 // development hook: bit 0 = the TMA producers stop loading after the first ring fill (timing experiment only: results are garbage)
 extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_umma_flags(int flags) { rmnet::g_dbg_flags = flags; }
+// chain stamps (common.cuh RMNET_DEV_STAMPS): a device array of 16 u64 (even slots = min-initialised starts, see tools/chain_timeline.py)
+namespace rmnet {
+void dev_set_chain_stamps_att_map(unsigned long long *);
+void dev_set_chain_stamps_bank(unsigned long long *);
+void dev_set_chain_stamps_merge(unsigned long long *);
+}
+extern "C" __attribute__((visibility("default"))) void rmnet_debug_set_chain_stamps(unsigned long long *p) {
+  rmnet::dev_set_chain_stamps_att_map(p); rmnet::dev_set_chain_stamps_bank(p); rmnet::dev_set_chain_stamps_merge(p); rmnet::dev_set_chain_stamps_umma(p);
+}
 #endif  // RMNET_DEV

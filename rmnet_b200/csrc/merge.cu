@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 namespace rmnet {
+RMNET_DEV_STAMPS(merge)
 namespace {
 
 constexpr int kMergeThreads = 128;
@@ -36,6 +37,7 @@ __global__ void __launch_bounds__(kMergeThreads)
 merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n_obj, int n_splits,
              const int *__restrict__ sched_ns, const float *__restrict__ opart, const float *__restrict__ ml, int nq_pad,
              float *__restrict__ mem_val, int n_gather_tiles) {
+  DEV_STAMP_MIN(7);
   const int N = h * w;
   const int o = blockIdx.z;
   const int c0 = blockIdx.y * kChPerCta;
@@ -93,82 +95,101 @@ merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n
         }
       }
     }
+    DEV_STAMP_MAX(10);
     return;
   }
 
   // ------------------------------ gather role ------------------------------
   // CTA = 32 compact queries x 32 channels: warp k owns channels [8k, 8k+8) of the same 32 queries.
+  // Before the dependency wait: everything that comes from further up the chain (rectangles: region kernel; counters
+  // and the plan's split counts: pack kernel -- both complete before the read kernel, our predecessor, could trigger us).
   const int count = rect_cells(qrect);
   if ((int)blockIdx.x * kQueriesPerCta >= count) return;  // CTA-uniform
-  // Chained launch: the partial results below come from the read kernel.
-  pdl_wait();
   const int n = (int)blockIdx.x * kQueriesPerCta + (tid & 31);  // compact query index
-  if (n >= count) return;
   const int cw = c0 + (tid >> 5) * 8;  // first channel of this warp
-  const int pos = rect_pos(qrect, n, w);
   const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
   const int half = c0 / (RMNET_CV / 2);
   if (sched_ns) n_splits = __ldg(sched_ns + o);  // KV chunks the persistent tcgen05 kernel used for this object
   const unsigned ml_stride = (unsigned)n_obj * 2u * (unsigned)nq_pad;        // float2 units between splits
   const unsigned op_stride = (unsigned)n_obj * RMNET_CV * (unsigned)nq_pad;  // floats between splits
-  const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad + n;
+  const bool live = n < count;
+  const int nn = live ? n : count - 1;  // dead lanes of the last tile shadow a live query (no divergent exit before the wait)
+  const int pos = rect_pos(qrect, nn, w);
+  const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad + nn;
+  const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)cw) * (unsigned)nq_pad + nn;
+  float *outp = out_o + (unsigned)cw * uN + pos;
+  // Chained launch: the partial results below come from the read kernel.
+  pdl_wait();
+  DEV_STAMP_MIN(8);
+  // ONE round trip: the statistics of all splits and the partial numerators of the first eight splits x eight channels
+  // are requested together (72-80 independent loads per thread); a split that saw no cells left its numerators unwritten,
+  // so what was loaded for it is replaced by zero, not multiplied by it.
+  float2 st[READ_MAX_SPLITS];
+#pragma unroll
+  for (int s = 0; s < READ_MAX_SPLITS; ++s) st[s] = (s < n_splits) ? ld_dep(mlp + (unsigned)s * ml_stride) : make_float2(-INFINITY, 0.f);
+  float v[8][8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float *q = opb + (unsigned)u * op_stride;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[u][k] = (u < n_splits) ? ld_dep(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
+  }
   float wgt[READ_MAX_SPLITS];
   {
-    float2 st[READ_MAX_SPLITS];
-#pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; ++s) st[s] = (s < n_splits) ? __ldg(mlp + (unsigned)s * ml_stride) : make_float2(-INFINITY, 0.f);
     float m_star = Z > 0 ? 0.f : -INFINITY;
 #pragma unroll
     for (int s = 0; s < READ_MAX_SPLITS; ++s) m_star = fmaxf(m_star, st[s].x);
     float L = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
 #pragma unroll
     for (int s = 0; s < READ_MAX_SPLITS; ++s) {
-      wgt[s] = (st[s].x == -INFINITY) ? 0.f : ex2f(st[s].x - m_star);  // a split that saw no cells left its numerators unwritten
+      wgt[s] = (st[s].x == -INFINITY) ? 0.f : ex2f(st[s].x - m_star);
       L = fmaf(st[s].y, wgt[s], L);
     }
     const float inv_l = 1.0f / L;
 #pragma unroll
     for (int s = 0; s < READ_MAX_SPLITS; ++s) wgt[s] *= inv_l;  // fold the normalisation into the split weights
   }
-  const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)cw) * (unsigned)nq_pad + n;
-  float *outp = out_o + (unsigned)cw * uN + pos;
-  // 8 channels x 8 splits = 64 independent loads in flight: one round trip for the usual split counts
   float num[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) num[k] = 0.f;
 #pragma unroll
-  for (int s0 = 0; s0 < READ_MAX_SPLITS; s0 += 8) {
-    if (s0 >= n_splits) break;
-    float v[8][8];
+  for (int u = 0; u < 8; ++u)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) num[k] = fmaf(wgt[u] != 0.f ? v[u][k] : 0.f, wgt[u], num[k]);
+  if (n_splits > 8) {
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const float *q = opb + (unsigned)(s0 + u) * op_stride;
+      const float *q = opb + (unsigned)(8 + u) * op_stride;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) v[u][k] = (wgt[s0 + u] != 0.f) ? __ldg(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
+      for (int k = 0; k < 8; ++k) v[u][k] = (wgt[8 + u] != 0.f) ? ld_dep(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u)
 #pragma unroll
-      for (int k = 0; k < 8; ++k) num[k] = fmaf(v[u][k], wgt[s0 + u], num[k]);
+      for (int k = 0; k < 8; ++k) num[k] = fmaf(v[u][k], wgt[8 + u], num[k]);
   }
+  if (live) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) outp[(unsigned)k * uN] = num[k];
+    for (int k = 0; k < 8; ++k) outp[(unsigned)k * uN] = num[k];
+  }
+  DEV_STAMP_MAX(9);
 }
 
 }  // namespace
 
+// fill_uniform = false: the uniform rows have been written by the read kernel (memory_read_umma.cu), gather role only.
 int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
-                 const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st) {
+                 const ReadWorkspace &W, float *mem_val, bool fill_uniform, bool pdl, cudaStream_t st) {
   const int N = h * w;
   const bool vec = N % 4 == 0 && ((uintptr_t)mem_val % 16 == 0);
   const int *ns = device_sched ? W.sched : nullptr;
   const int n_gather_tiles = W.nq_pad / kQueriesPerCta;
   if (vec) {
-    dim3 grid(n_gather_tiles + cdiv(N, 128), RMNET_CV / kChPerCta, n_obj);
+    dim3 grid(n_gather_tiles + (fill_uniform ? cdiv(N, 128) : 0), RMNET_CV / kChPerCta, n_obj);
     RMNET_CUDA(launch_kernel(merge_kernel<4>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, n_obj, n_splits, ns,
                              W.opart, W.ml, W.nq_pad, mem_val, n_gather_tiles));
   } else {
-    dim3 grid(n_gather_tiles + cdiv(N, 128), RMNET_CV / kChPerCta, n_obj);
+    dim3 grid(n_gather_tiles + (fill_uniform ? cdiv(N, 128) : 0), RMNET_CV / kChPerCta, n_obj);
     RMNET_CUDA(launch_kernel(merge_kernel<1>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, n_obj, n_splits, ns,
                              W.opart, W.ml, W.nq_pad, mem_val, n_gather_tiles));
   }

@@ -4,6 +4,7 @@ Every function takes CUDA float32 tensors, allocates outputs with torch's cachin
 pointers + the current stream to librmnet_b200.so, and never synchronises.  Error behaviour mirrors the
 reference's CHECK_INPUT (reg_att_map_generator_cuda.cpp:14-19): non-CUDA / non-contiguous inputs raise RuntimeError.
 """
+import ctypes
 import math
 
 import torch
@@ -285,6 +286,26 @@ class MemoryBank:
                                                self.w, self.elem_format, precision, impl, stages, out.data_ptr(), self._ws_ptr,
                                                self._ws.numel() - 1024, _stream(self.device)), "bank_memory_read")
         return out
+
+    def read_plan(self, n_obj):
+        """The work plan of the last read / frame step on this bank (sched.cuh): (ns [n_obj], per-CTA piece lists) with
+        pieces as tuples (object, query_tile, half, slot, first_tile, tiles, stored_cells).  Introspection / tests."""
+        import numpy as np
+        ns = np.zeros(n_obj, np.int32)
+        hdr = np.zeros((256, 2), np.int32)
+        cap = 1 << 16
+        pcs = np.zeros((cap, 4), np.int32)
+        n_ctas = ctypes.c_int(0)
+        with torch.cuda.device(self.device):
+            check(lib().rmnet_memory_read_plan_host(self._ws_ptr, n_obj, self.h, self.w, ns.ctypes.data, hdr.ctypes.data,
+                                                    pcs.ctypes.data, cap, ctypes.byref(n_ctas), _stream(self.device)),
+                  "memory_read_plan_host")
+        lists = []
+        for c in range(n_ctas.value):
+            n, off = int(hdr[c, 0]), int(hdr[c, 1])
+            lists.append([(int(v[0]) & 255, (int(v[0]) >> 8) & 255, (int(v[0]) >> 16) & 15, (int(v[0]) >> 20) & 0xfff,
+                           int(v[1]), int(v[2]), int(v[3])) for v in pcs[off:off + n]])
+        return ns, lists
 
     def stats(self):
         import numpy as np

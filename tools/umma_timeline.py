@@ -17,7 +17,7 @@ for wlname in ("c2", "c3"):
         d = D(pool["frames"][t]); rm.memorize(d["k4"], d["v4"], d["mask"][None], commit=True)
     d = D(pool["frames"][T - 1])
     for _ in range(3): rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
-    dbg = torch.zeros(8448 + 148 * 32 + 64, device=dev)
+    dbg = torch.zeros(8448 + 148 * 64 + 64, device=dev)
     torch.cuda.synchronize()
     standalone = len(sys.argv) > 1 and sys.argv[1] == "standalone"
     if standalone:   # the read kernel launched alone (no PDL chain): what bench.py's roofline times
@@ -34,7 +34,9 @@ for wlname in ("c2", "c3"):
     torch.cuda.synchronize()
     L.rmnet_debug_set_umma_flags(0)
     L.rmnet_debug_set_umma_dump(None)
-    ts = dbg[8448:8448 + 148 * 32].view(torch.int64).view(148, 16).cpu().numpy()
+    ts = dbg[8448:8448 + 148 * 64].view(torch.int64).view(148, 32).cpu().numpy()
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    np.save(os.path.join(ROOT, 'gpurun_out', f"timeline_{wlname}_{'standalone' if standalone else 'chained'}.npy"), ts)
     live = ts[:, 6] > 0
     t = ts[live]
     rel = (t[:, 1:7] - t[:, :1]).astype(np.float64)
@@ -45,7 +47,7 @@ for wlname in ("c2", "c3"):
         print(f"   {nm:30s} {np.median(rel[:, i]):9.0f} {rel[:, i].max():9.0f}   (+{np.median(rel[:, i]) - prev:7.0f})")
         prev = np.median(rel[:, i])
     ex = (t[:, 8:15] - t[:, :1]).astype(np.float64)
-    for i, nm in enumerate(["sched begin", "sched end", "alloc begin", "alloc end", "iter.next done", "Q loads issued", "Q converted+stored (before wait::st)"]):
+    for i, nm in enumerate(["setup begin", "plan loaded (after the dependency wait)", "-", "TMEM allocated", "softmax warpgroup starts", "Q loads issued", "Q converted+stored (before wait::st)"]):
         print(f"      .. {nm:38s} {np.median(ex[:, i]):9.0f}")
     order = np.argsort(rel[:, 5])
     print("   tiles of the first item, by CTA end time:", " ".join(f"{int(a)}" for a in t[order, 7][::4]))
