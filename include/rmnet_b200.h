@@ -72,9 +72,9 @@ RMNET_API int rmnet_has_umma(void);
  *   mask     [B,K,H,W] f32
  *   bboxes   [B,K,4]   i32 = (x_min, x_max, y_min, y_max) inclusive; channel 0 -> (0,0,0,0)
  *   att_full [B,K,H,W] f32 in {0,1}, nullable (every element is written: no pre-zeroing needed)
- *   workspace: rmnet_reg_att_map_workspace_bytes(B,K) bytes, ZERO-FILLED ONCE by the caller at
- *              allocation; the kernels leave it zeroed again (self-cleaning), so it can be reused
- *              by consecutive calls on the same stream.
+ *   workspace: rmnet_reg_att_map_workspace_bytes(B,K) bytes, 16-byte aligned, ZERO-FILLED ONCE by the
+ *              caller at allocation; the kernels leave it zeroed again (self-cleaning), so it can be
+ *              reused by consecutive calls on the same stream.
  * ------------------------------------------------------------------------------------------- */
 RMNET_API size_t rmnet_reg_att_map_workspace_bytes(int B, int K);
 RMNET_API int rmnet_reg_att_map_forward(const float *mask, int B, int K, int H, int W, float prob_threshold,

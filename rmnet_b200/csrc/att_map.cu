@@ -17,6 +17,10 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWsIntsPerChannel = 8;  // cnt, inv_xmin, xmax, inv_ymin, ymax, ticket, -, -
+// The fused kernel's ~600 CTAs publish into kWsCopies copies of the accumulator array (CTA c into copy c % kWsCopies):
+// atomics on one 32-byte sector serialise in L2, and with one copy the 5 words of a channel took ~3 000 of them -- 4 to
+// 6 us between the last CTA leaving the pixel loop and the last ticket.  The finalising CTA folds the copies.
+constexpr int kWsCopies = 16;
 
 // ---- per-thread bbox accumulator -------------------------------------------------------------
 struct BoxAcc {
@@ -73,12 +77,13 @@ __device__ __forceinline__ void write_rect(const BoxFinalize &f, long long ch, c
 
 // reg_att_map_generator.cu:55-77 -- loosen / clamp, or full frame when too few points.
 // Reads AND clears the workspace accumulators (self-cleaning).
-__device__ __forceinline__ void finalize_channel(int *ws, int *bboxes, long long ch, const BoxFinalize &f) {
-  int cnt = atomicExch(ws + 0, 0);
-  int xmin = 32767 - atomicExch(ws + 1, 0) + f.off_x;
-  int xmax = atomicExch(ws + 2, 0) + f.off_x;
-  int ymin = 32767 - atomicExch(ws + 3, 0) + f.off_y;
-  int ymax = atomicExch(ws + 4, 0) + f.off_y;
+// From the folded accumulators of one channel (mins stored inverted) to the outputs.
+__device__ __forceinline__ void finalize_values(int cnt, int a1, int a2, int a3, int a4, int *bboxes, long long ch,
+                                                const BoxFinalize &f) {
+  int xmin = 32767 - a1 + f.off_x;
+  int xmax = a2 + f.off_x;
+  int ymin = 32767 - a3 + f.off_y;
+  int ymax = a4 + f.off_y;
   int4 r;
   if (cnt < f.n_pts_threshold || f.force_full) {
     r = make_int4(0, f.Wf - 1, 0, f.Hf - 1);
@@ -90,6 +95,12 @@ __device__ __forceinline__ void finalize_channel(int *ws, int *bboxes, long long
   }
   reinterpret_cast<int4 *>(bboxes)[ch] = r;  // bboxes are [.,4] i32, 16 B aligned per entry
   write_rect(f, ch, r, false);
+}
+// Reads AND clears the workspace accumulators of one channel (self-cleaning), single-copy form.
+__device__ __forceinline__ void finalize_channel(int *ws, int *bboxes, long long ch, const BoxFinalize &f) {
+  const int cnt = atomicExch(ws + 0, 0), a1 = atomicExch(ws + 1, 0), a2 = atomicExch(ws + 2, 0), a3 = atomicExch(ws + 3, 0),
+            a4 = atomicExch(ws + 4, 0);
+  finalize_values(cnt, a1, a2, a3, a4, bboxes, ch, f);
 }
 __device__ __forceinline__ void finalize_channel0(int *bboxes, long long ch, const BoxFinalize &f) {
   reinterpret_cast<int4 *>(bboxes)[ch] = make_int4(0, 0, 0, 0);  // channel 0 keeps the zero fill (.cu:104)
@@ -407,14 +418,16 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
     }
   }
   __syncthreads();
+  DEV_STAMP_MIN(37); DEV_STAMP_MAX(36);
   // CTA -> global workspace: set 0 (warped) at ws_b, set 1 (direct) right behind it.  Only the threads that publish
   // accumulators pay for the fence (a device-wide fence by all 256 threads was 13 % of this kernel's stall samples).
   int *ws_b = ws + (long long)b * 2 * (K + 1) * kWsIntsPerChannel;
+  const long long copy_stride = (long long)gridDim.y * 2 * (K + 1) * kWsIntsPerChannel;  // ints between two copies of the array
   bool published = false;
   for (int e = threadIdx.x; e < (DIRECT ? 2 : 1) * K; e += kThreads) {
     const int set = e / K, i = e - set * K;
     if (i >= 1 && s_acc[e * 5] > 0) {
-      int *w = ws_b + (set * (K + 1) + i) * kWsIntsPerChannel;
+      int *w = ws_b + (blockIdx.x % kWsCopies) * copy_stride + (set * (K + 1) + i) * kWsIntsPerChannel;
       atomicAdd(w + 0, s_acc[e * 5 + 0]);
       atomicMax(w + 1, s_acc[e * 5 + 1]);
       atomicMax(w + 2, s_acc[e * 5 + 2]);
@@ -430,14 +443,42 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
     s_last = (ticket == (int)gridDim.x - 1);
   }
   __syncthreads();
+  DEV_STAMP_MAX(38);
   if (s_last) {
     __threadfence();
-    for (int e = threadIdx.x; e < (DIRECT ? 2 : 1) * K; e += kThreads) {
-      const int set = e / K, i = e - set * K;
-      int *bb = set ? bboxes_direct : bboxes_warp;
-      const BoxFinalize &f = set ? fin_direct : fin_warp;
-      if (i == 0) finalize_channel0(bb, (long long)b * K, f);
-      else finalize_channel(ws_b + (set * (K + 1) + i) * kWsIntsPerChannel, bb, (long long)b * K + i, f);
+    // fold the kWsCopies copies: 16 consecutive lanes read-and-clear one channel's words of the 16 copies (one round
+    // trip for the whole array), a half-warp shuffle reduction folds them, the copy-0 lane finalises the channel
+    static_assert(kWsCopies == 16 && kThreads % kWsCopies == 0, "half-warp fold");
+    const int n_e = (DIRECT ? 2 : 1) * K;
+    for (int e0 = 0; e0 < n_e; e0 += kThreads / kWsCopies) {
+      const int e = e0 + threadIdx.x / kWsCopies, c = threadIdx.x % kWsCopies;
+      const bool act = e < n_e;
+      const int set = act ? e / K : 0, i = act ? e - set * K : 0;
+      int v[5] = {0, 0, 0, 0, 0};
+      if (act && i >= 1) {
+        // every publisher fenced before it took its ticket and ours was the last: plain (L2) loads see the final values
+        // and plain stores may clear them -- 5 atomic exchanges per word made this fold a 3 us tail of its own
+        int *w = ws_b + c * copy_stride + (set * (K + 1) + i) * kWsIntsPerChannel;
+        const int4 lo = ld_dep(reinterpret_cast<const int4 *>(w));
+        v[4] = ld_dep(w + 4);
+        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+        if (v[0] != 0) {  // (a copy that saw no hit is still all zero)
+          *reinterpret_cast<int4 *>(w) = make_int4(0, 0, 0, 0);
+          w[4] = 0;
+        }
+      }
+#pragma unroll
+      for (int d = kWsCopies / 2; d >= 1; d >>= 1) {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+#pragma unroll
+        for (int u = 1; u < 5; ++u) v[u] = max(v[u], __shfl_xor_sync(0xffffffffu, v[u], d));
+      }
+      if (act && c == 0) {
+        int *bb = set ? bboxes_direct : bboxes_warp;
+        const BoxFinalize &f = set ? fin_direct : fin_warp;
+        if (i == 0) finalize_channel0(bb, (long long)b * K, f);
+        else finalize_values(v[0], v[1], v[2], v[3], v[4], bb, (long long)b * K + i, f);
+      }
     }
     if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);
   }
@@ -479,6 +520,7 @@ int check_common(const void *mask, int B, int K, int H, int W, const int *bboxes
   RMNET_CHECK_ARG(H <= 32767 && W <= 32767, "H, W must be <= 32767 (reference min-init, reg_att_map_generator.cu:32)");
   RMNET_CHECK_ARG(B <= 65535, "B too large");
   RMNET_CHECK_ARG((uintptr_t)bboxes % 16 == 0, "bboxes must be 16-byte aligned");
+  RMNET_CHECK_ARG((uintptr_t)ws % 16 == 0, "workspace must be 16-byte aligned");
   if (ws_bytes < rmnet_reg_att_map_workspace_bytes(B, K)) {
     set_error("workspace too small: %zu < %zu", ws_bytes, rmnet_reg_att_map_workspace_bytes(B, K));
     return RMNET_E_WORKSPACE;
@@ -494,7 +536,7 @@ using namespace rmnet;
 extern "C" {
 
 size_t rmnet_reg_att_map_workspace_bytes(int B, int K) {
-  return (size_t)B * 2 * (K + 1) * kWsIntsPerChannel * sizeof(int);  // two accumulator sets (warped, direct)
+  return (size_t)kWsCopies * B * 2 * (K + 1) * kWsIntsPerChannel * sizeof(int);  // two accumulator sets (warped, direct) x copies
 }
 
 static void make_finalize(BoxFinalize &fin, bool padded, int H, int W, int pad_l, int pad_r, int pad_t, int pad_b, float thr,

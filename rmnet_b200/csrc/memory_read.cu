@@ -5,11 +5,11 @@ namespace rmnet {
 int launch_memory_read_simt(const BankView &bank, const float *q_key, long long q_obj_stride, const int *q_rects,
                             int n_obj, int h, int w, int fmt, int precision, int n_splits, const ReadWorkspace &W,
                             cudaStream_t st);
-int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, const int *q_rects,
-                            int h, int w, float *mem_val, bool pdl, cudaStream_t st);
+int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, bool pdl,
+                            cudaStream_t st);
 int umma_grid_size();
 int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
-                 const ReadWorkspace &W, float *mem_val, bool fill_uniform, bool pdl, cudaStream_t st);
+                 const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st);
 bool umma_supported(int cap_cells);
 int launch_attention_probs(const float *m_key, const float *q_key, int n, int M, int N, float *p, cudaStream_t st);
 
@@ -78,23 +78,12 @@ int bank_memory_read_impl(const void *bank, size_t bank_bytes, int n_slots, int 
   }
   if (!(stages & RMNET_STAGE_PARTIAL)) {
   } else if (umma)
-#ifdef RMNET_EXP_NO_BGFILL
-    rc = launch_memory_read_umma(bv, n_obj, elem_format, precision, W, q_rects, h, w, nullptr, chained, st);
-#else
-    rc = launch_memory_read_umma(bv, n_obj, elem_format, precision, W, q_rects, h, w, mem_val, chained, st);
-#endif
+    rc = launch_memory_read_umma(bv, n_obj, elem_format, precision, W, chained, st);
   else
     rc = launch_memory_read_simt(bv, q_key, q_obj_stride, q_rects, n_obj, h, w, elem_format, precision, n_splits, W, st);
   if (rc || !(stages & RMNET_STAGE_MERGE)) return rc;
   // the merge is a programmatic dependent of the tcgen05 kernel whenever both run in this call
-  // (the tcgen05 kernel writes the uniform rows of mem_val itself; the FFMA path leaves them to the merge kernel)
-  return launch_merge(bv, q_rects, n_obj, h, w, n_splits, umma, W, mem_val, /*fill_uniform=*/
-#ifdef RMNET_EXP_NO_BGFILL
-                      true,
-#else
-                      !umma,
-#endif
-                      umma && (stages & RMNET_STAGE_PARTIAL), st);
+  return launch_merge(bv, q_rects, n_obj, h, w, n_splits, umma, W, mem_val, umma && (stages & RMNET_STAGE_PARTIAL), st);
 }
 
 }  // namespace

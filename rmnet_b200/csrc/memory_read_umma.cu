@@ -196,107 +196,6 @@ struct PieceIter {
   }
 };
 
-// Uniform rows of mem_val (an out-of-region query reads sum(V) / M, merge.cu's header), written in the background by the
-// otherwise idle warp 3 of every CTA while the tensor pipe works: 12.6 MB of stores at the headline size that the merge
-// kernel used to issue after the read (its CTAs cannot start earlier: every SM is busy with a read CTA until the end).
-struct UniformFill {
-  const long long *vsum;  // BankView::vsum
-  const int *meta;        // BankView::meta
-  const int *q_rects;     // [n_obj][4] or nullptr (dense: nothing to fill)
-  float *mem_val;         // nullptr = no fill
-  int h, w, n_slots, vec4;
-};
-// One warp; a single warp issues a dependent instruction every ~5 cycles, so the instruction count per stored byte is what
-// matters here.  CTA `cta` owns a CONTIGUOUS block of rows (object, channel) -- at most two objects -- taken 32 at a time:
-// lane r fetches the value of row r of the batch (one round trip for the batch), then the warp stores row after row.  Per
-// object the lane's "cell is inside the query rectangle" bits are computed once (4 bits per 128-cell step of the row, up
-// to 32 steps = 4 096 cells in two 64-bit registers), so a row costs ~5 instructions per 512-byte store.
-__device__ __forceinline__ void fill_uniform_rows(const UniformFill &f, int cta, int n_ctas, int n_obj) {
-  if (!f.mem_val || !f.q_rects) return;
-  const int lane = threadIdx.x & 31;
-  const int N = f.h * f.w;
-  const int n_rows = n_obj * RMNET_CV;
-  const int per_cta = (n_rows + n_ctas - 1) / n_ctas;
-  const int row_end = min(n_rows, (cta + 1) * per_cta);
-  const int n_steps = (N + 127) / 128;
-  const bool fast = f.vec4 && n_steps <= 32;
-  int cur_o = -1;
-  int4 qr = make_int4(0, 0, 0, 0);
-  bool skip = true;
-  unsigned long long in_lo = 0ull, in_hi = 0ull;
-  for (int r0 = cta * per_cta; r0 < row_end; r0 += 32) {
-    float my_u = 0.f;
-    if (r0 + lane < row_end) {
-      const int row = r0 + lane;
-      const int o = row / RMNET_CV, ch = row - o * RMNET_CV;
-      const int *meta = f.meta + o * 8;
-      const int M = ld_dep(meta + META_ZEROS_C) + ld_dep(meta + META_ZEROS_T) + ld_dep(meta + META_CELLS_C) + ld_dep(meta + META_CELLS_T);
-      const long long *vs_c = f.vsum + (size_t)o * RMNET_CV, *vs_t = f.vsum + ((size_t)f.n_slots + o) * RMNET_CV;
-      my_u = (__ll2float_rn(ld_dep(vs_c + ch) + ld_dep(vs_t + ch)) * VSUM_INV_SCALE) * (1.0f / (float)M);  // merge.cu's expression
-    }
-    const int nb = min(32, row_end - r0);
-    for (int j = 0; j < nb; ++j) {
-      const int row = r0 + j;
-      const float u = __shfl_sync(0xffffffffu, my_u, j);
-      const int o = row / RMNET_CV, ch = row - o * RMNET_CV;
-      if (o != cur_o) {
-        cur_o = o;
-        qr = __ldg(reinterpret_cast<const int4 *>(f.q_rects) + o);
-        skip = rect_cells(qr) == N;
-        if (fast && !skip) {
-          in_lo = in_hi = 0ull;
-          const int p0 = lane * 4;
-          int cy = p0 / f.w, cx = p0 - cy * f.w;          // the lane's quad of step 0; every step advances it by 128 cells
-          const int dy = 128 / f.w, dx = 128 - dy * f.w;
-          for (int it = 0; it < n_steps; ++it) {
-            unsigned m = 15u;  // cells beyond N count as "inside": never stored
-            if (it * 128 + p0 < N) {
-              int ey = cy, ex = cx;
-              m = 0u;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (ex >= qr.x && ex <= qr.y && ey >= qr.z && ey <= qr.w) m |= 1u << e;
-                if (++ex == f.w) { ex = 0; ++ey; }
-              }
-            }
-            if (it < 16) in_lo |= (unsigned long long)m << (4 * it);
-            else in_hi |= (unsigned long long)m << (4 * (it - 16));
-            cy += dy; cx += dx;
-            if (cx >= f.w) { cx -= f.w; ++cy; }
-          }
-        }
-      }
-      if (skip) continue;
-      float *out = f.mem_val + ((size_t)o * 2 * RMNET_CV + ch) * N + lane * 4;
-      if (fast) {
-        unsigned long long bits = in_lo;
-#pragma unroll 1
-        for (int it0 = 0; it0 < n_steps; it0 += 16, bits = in_hi) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (it0 + i < n_steps) {
-              const unsigned m = (unsigned)(bits >> (4 * i)) & 15u;
-              float *q = out + (it0 + i) * 128;
-              if (m == 0u) {
-                *reinterpret_cast<float4 *>(q) = make_float4(u, u, u, u);
-              } else if (m != 15u) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) if (!((m >> e) & 1u)) q[e] = u;
-              }
-            }
-          }
-        }
-      } else {
-        out -= lane * 4;
-        for (int p = lane; p < N; p += 32) {
-          const int cy = p / f.w, cx = p - cy * f.w;
-          if (!(cx >= qr.x && cx <= qr.y && cy >= qr.z && cy <= qr.w)) out[p] = u;
-        }
-      }
-    }
-  }
-}
-
 // USE_LO: the score product Q.K^T takes the 3-term hi/lo split (K lo plane loaded, Q lo plane in TMEM);
 // PV_LO : so does the P.V product (V lo plane loaded, P split into hi/lo).  (true, true) = strict, (false, false) = fast,
 // (true, false) = mixed: scores -- whose error is exponentiated -- keep 22 mantissa bits, P and V go through one product.
@@ -306,7 +205,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
                         const __grid_constant__ CUtensorMap map_vhi, const __grid_constant__ CUtensorMap map_vlo,
                         const uint16_t *__restrict__ qhi, const uint16_t *__restrict__ qlo,
                         const int2 *__restrict__ plan_hdr, const int4 *__restrict__ plan_pieces,
-                        float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj, const UniformFill fill,
+                        float *__restrict__ opart, float *__restrict__ ml, int nq_pad, int n_obj,
                         float *__restrict__ dbg_arg, int dbg_flags_arg) {
   // Development instrumentation (S dump, clock64 stamps, the no-TMA experiment) exists only in -DRMNET_DEV builds
   // (`make DEV=1`); in the release build the hooks are compile-time nulls and every branch on them is dead code.
@@ -368,10 +267,8 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (s_hdr.x == 0) {  // no pieces for this CTA (uniform): give the TMEM back, do the CTA's share of the uniform rows, leave
+  if (s_hdr.x == 0) {  // no pieces for this CTA (uniform): give the TMEM back and leave
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(bars->tmem_base), "r"(512u) : "memory");
-    if (warp == 4) pdl_trigger();
-    if (warp == 3) fill_uniform_rows(fill, (int)blockIdx.x, (int)gridDim.x, n_obj);
     return;
   }
   const uint32_t tmem = bars->tmem_base;
@@ -486,9 +383,6 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
         if (st < pc.n_it) issue_qk();
       }
     }
-  } else if (warp == 3) {
-    // ================= background: the uniform rows of mem_val =================
-    fill_uniform_rows(fill, (int)blockIdx.x, (int)gridDim.x, n_obj);
   } else if (warp >= 4) {
     // ================= softmax / correction / epilogue warpgroup: thread <-> query row <-> TMEM lane =================
     const int row = threadIdx.x - 128;                  // 0..127
@@ -733,10 +627,8 @@ int umma_grid_size() {
 
 // The work plan (W.plan_hdr / W.plan_pieces / W.sched) must have been written by the launch right before this one in the
 // stream: the pack kernel of rmnet_frame_step or the query-side launch of rmnet_bank_memory_read (bank.cu: ROLE_PLAN).
-// q_rects / h / w / mem_val: for the uniform rows of mem_val (cells outside an object's query rectangle), which the kernel
-// writes in the background; mem_val == nullptr skips them.
-int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, const int *q_rects,
-                            int h, int w, float *mem_val, bool pdl, cudaStream_t st) {
+int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precision, const ReadWorkspace &W, bool pdl,
+                            cudaStream_t st) {
   RMNET_CHECK_ARG(bank.cap % 64 == 0, "tcgen05 path needs cap_cells %% 64 == 0 (got %d)", bank.cap);
   RMNET_CHECK_ARG(n_obj <= SCHED_MAX_OBJ, "tcgen05 path supports at most %d objects per call", (int)SCHED_MAX_OBJ);
   // The four tensor maps depend only on the bank (base pointers, capacity, slots): encode once per bank and thread.
@@ -765,10 +657,6 @@ int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precis
   dim3 grid(n_sms);
   RMNET_CHECK_ARG(n_sms <= PLAN_HDR_CTAS && W.nq_pad / 128 <= 256, "tcgen05 path: %d SMs / %d query tiles exceed the plan's limits", n_sms, W.nq_pad / 128);
   const bool lo = precision != RMNET_PREC_SINGLE, plo = precision == RMNET_PREC_SPLIT3;
-  UniformFill fill;
-  fill.vsum = bank.vsum; fill.meta = bank.meta; fill.q_rects = q_rects; fill.mem_val = mem_val;
-  fill.h = h; fill.w = w; fill.n_slots = bank.n_slots;
-  fill.vec4 = ((h * w) % 4 == 0 && (uintptr_t)mem_val % 16 == 0) ? 1 : 0;
 #define RMNET_LAUNCH_UMMA(F, L, P)                                                                                          \
   do {                                                                                                                   \
     static bool attr_set[64] = {};                                                                                       \
@@ -781,7 +669,7 @@ int launch_memory_read_umma(const BankView &bank, int n_obj, int fmt, int precis
     }                                                                                                                    \
     RMNET_CUDA(launch_kernel(memory_read_umma_kernel<F, L, P>, grid, dim3(kThreads), SMEM_BYTES, st, pdl, mkh, mkl, mvh, mvl, \
                              W.qhi, W.qlo, reinterpret_cast<const int2 *>(W.plan_hdr),                                  \
-                             reinterpret_cast<const int4 *>(W.plan_pieces), W.opart, W.ml, W.nq_pad, n_obj, fill, g_dbg,\
+                             reinterpret_cast<const int4 *>(W.plan_pieces), W.opart, W.ml, W.nq_pad, n_obj, g_dbg,      \
                              g_dbg_flags));                                                                              \
   } while (0)
   if (fmt == 0 && plo) RMNET_LAUNCH_UMMA(0, true, true);

@@ -26,36 +26,63 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-// Two CTA roles in one launch, both 128 threads x 32 channels of one object:
-//   gather (blockIdx.x < n_gather_tiles): 32 in-region queries (compact indices) x 32 channels; thread = one query x 8
-//       channels: statistics of all splits in one batch of loads, then the partial numerators of eight splits x eight
-//       channels in one batch (64 independent loads in flight), scattered to the query's cell.
-//   fill   (blockIdx.x >= n_gather_tiles): thread = VEC consecutive cells x 8 channels: the uniform rows of the cells
-//       outside the query region (128-bit stores).  Needs only the bank, so in a chained launch it runs before the wait.
-template <int VEC>
-__global__ void __launch_bounds__(kMergeThreads)
-merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n_obj, int n_splits,
-             const int *__restrict__ sched_ns, const float *__restrict__ opart, const float *__restrict__ ml, int nq_pad,
-             float *__restrict__ mem_val, int n_gather_tiles) {
-  DEV_STAMP_MIN(7);
-  const int N = h * w;
-  const int o = blockIdx.z;
-  const int c0 = blockIdx.y * kChPerCta;
-  const int tid = threadIdx.x;
-  const int4 qrect = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o) : make_int4(0, w - 1, 0, h - 1);
-  const unsigned uN = (unsigned)N;
-  float *out_o = mem_val + (unsigned)o * 2u * RMNET_CV * uN;
-  const int *meta = bank.meta + o * 8;
+// A persistent grid walking a device-built work list (the query rectangles are only known on the device; a grid sized for
+// the whole frame per object was mostly CTAs that exit at once, dispatched in two to three waves):
+//   fill items   (before the dependency wait: they need only the bank): 128 cells x 32 channels of one object, thread =
+//       VEC consecutive cells x 8 channels: the uniform rows of the cells outside the query region (128-bit stores);
+//   gather items (after the wait): 32 in-region queries (compact indices) x 32 channels; thread = one query x 8 channels.
+//       Two passes over the splits with run-time trip counts -- the reference maximum, then weights, normaliser and the
+//       weighted numerators four splits (36 independent loads) at a time -- in 64 registers, so that the whole list is
+//       resident at once (8 CTAs per SM); the former single batch of 80 loads per thread needed 144 registers and ran
+//       in two to three rounds.
+struct MergeList {
+  int4 rect[SCHED_MAX_OBJ];
+  int fill_pre[SCHED_MAX_OBJ + 1], gather_pre[SCHED_MAX_OBJ + 1];
+};
 
-  if ((int)blockIdx.x >= n_gather_tiles) {
-    // ------------------------------ fill role ------------------------------
-    const int p_tile = ((int)blockIdx.x - n_gather_tiles) * 128;
-    // tiles entirely inside the query region have nothing to fill (rows of the rectangle are usually narrower than a
-    // tile, so this only triggers for dense reads)
-    if (rect_cells(qrect) == N) return;
-    __shared__ float s_uniform[kChPerCta];  // sum(V)/M of the CTA's channels (out-of-region read)
+template <int VEC>
+__global__ void __launch_bounds__(kMergeThreads, 8)
+merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n_obj, int o_base, int n_obj_total, int n_splits_arg,
+             const int *__restrict__ sched_ns, const float *__restrict__ opart, const float *__restrict__ ml, int nq_pad,
+             float *__restrict__ mem_val) {
+  DEV_STAMP_MIN(7);
+  __shared__ MergeList L;
+  __shared__ float s_uniform[kChPerCta];  // sum(V)/M of a fill item's channels (out-of-region read)
+  const int N = h * w;
+  const int tid = threadIdx.x;
+  const unsigned uN = (unsigned)N;
+  const int fill_tiles = (N + 127) / 128, ch_groups = RMNET_CV / kChPerCta;
+  // ---- work list.  Everything read here comes from further up the chain (rectangles: region kernel; counters and the
+  //      plan's split counts: pack kernel -- both complete before the read kernel, our predecessor, could trigger us).
+  if (tid < n_obj) {
+    const int4 r = q_rects ? __ldg(reinterpret_cast<const int4 *>(q_rects) + o_base + tid) : make_int4(0, w - 1, 0, h - 1);
+    const int count = rect_cells(r);
+    L.rect[tid] = r;
+    L.fill_pre[tid] = count == N ? 0 : fill_tiles * ch_groups;  // (a dense read has nothing to fill)
+    L.gather_pre[tid] = ((count + kQueriesPerCta - 1) / kQueriesPerCta) * ch_groups;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    int *pre = tid ? L.gather_pre : L.fill_pre;
+    int acc = 0;
+    for (int o = 0; o < n_obj; ++o) { const int c = pre[o]; pre[o] = acc; acc += c; }
+    pre[n_obj] = acc;
+  }
+  __syncthreads();
+
+  // ------------------------------ fill items ------------------------------
+  for (int item = blockIdx.x; item < L.fill_pre[n_obj]; item += gridDim.x) {
+    int ol = 0;
+    while (L.fill_pre[ol + 1] <= item) ++ol;
+    const int q = item - L.fill_pre[ol];
+    const int o = o_base + ol;
+    const int c0 = (q % ch_groups) * kChPerCta, p_tile = (q / ch_groups) * 128;
+    const int4 qrect = L.rect[ol];
+    const int *meta = bank.meta + o * 8;
+    float *out_o = mem_val + (unsigned)o * 2u * RMNET_CV * uN;
     const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
     const int M = Z + meta[META_CELLS_C] + meta[META_CELLS_T];
+    __syncthreads();  // (s_uniform of the previous item)
     if (tid < kChPerCta) {
       const long long *vs_c = bank.vsum + (size_t)o * RMNET_CV, *vs_t = bank.vsum + ((size_t)bank.n_slots + o) * RMNET_CV;
       s_uniform[tid] = (__ll2float_rn(vs_c[c0 + tid] + vs_t[c0 + tid]) * VSUM_INV_SCALE) * (1.0f / (float)M);
@@ -95,105 +122,90 @@ merge_kernel(BankView bank, const int *__restrict__ q_rects, int h, int w, int n
         }
       }
     }
-    DEV_STAMP_MAX(10);
-    return;
   }
+  DEV_STAMP_MAX(10);
+  if ((int)blockIdx.x >= L.gather_pre[n_obj]) return;  // (CTA-uniform) nothing to gather for this CTA
 
-  // ------------------------------ gather role ------------------------------
-  // CTA = 32 compact queries x 32 channels: warp k owns channels [8k, 8k+8) of the same 32 queries.
-  // Before the dependency wait: everything that comes from further up the chain (rectangles: region kernel; counters
-  // and the plan's split counts: pack kernel -- both complete before the read kernel, our predecessor, could trigger us).
-  const int count = rect_cells(qrect);
-  if ((int)blockIdx.x * kQueriesPerCta >= count) return;  // CTA-uniform
-  const int n = (int)blockIdx.x * kQueriesPerCta + (tid & 31);  // compact query index
-  const int cw = c0 + (tid >> 5) * 8;  // first channel of this warp
-  const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
-  const int half = c0 / (RMNET_CV / 2);
-  if (sched_ns) n_splits = __ldg(sched_ns + o);  // KV chunks the persistent tcgen05 kernel used for this object
-  const unsigned ml_stride = (unsigned)n_obj * 2u * (unsigned)nq_pad;        // float2 units between splits
-  const unsigned op_stride = (unsigned)n_obj * RMNET_CV * (unsigned)nq_pad;  // floats between splits
-  const bool live = n < count;
-  const int nn = live ? n : count - 1;  // dead lanes of the last tile shadow a live query (no divergent exit before the wait)
-  const int pos = rect_pos(qrect, nn, w);
-  const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad + nn;
-  const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)cw) * (unsigned)nq_pad + nn;
-  float *outp = out_o + (unsigned)cw * uN + pos;
-  // Chained launch: the partial results below come from the read kernel.
+  // ------------------------------ gather items ------------------------------
+  // Chained launch: the partial results come from the read kernel.  They are read with ld_dep (common.cuh).
   pdl_wait();
   DEV_STAMP_MIN(8);
-  // ONE round trip: the statistics of all splits and the partial numerators of the first eight splits x eight channels
-  // are requested together (72-80 independent loads per thread); a split that saw no cells left its numerators unwritten,
-  // so what was loaded for it is replaced by zero, not multiplied by it.
-  float2 st[READ_MAX_SPLITS];
-#pragma unroll
-  for (int s = 0; s < READ_MAX_SPLITS; ++s) st[s] = (s < n_splits) ? ld_dep(mlp + (unsigned)s * ml_stride) : make_float2(-INFINITY, 0.f);
-  float v[8][8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const float *q = opb + (unsigned)u * op_stride;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[u][k] = (u < n_splits) ? ld_dep(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
-  }
-  float wgt[READ_MAX_SPLITS];
-  {
+  for (int item = blockIdx.x; item < L.gather_pre[n_obj]; item += gridDim.x) {
+    int ol = 0;
+    while (L.gather_pre[ol + 1] <= item) ++ol;
+    const int q = item - L.gather_pre[ol];
+    const int o = o_base + ol;
+    const int c0 = (q % ch_groups) * kChPerCta, tile = q / ch_groups;
+    const int4 qrect = L.rect[ol];
+    const int count = rect_cells(qrect);
+    const int n = tile * kQueriesPerCta + (tid & 31);  // compact query index
+    if (n >= count) continue;
+    const int cw = c0 + (tid >> 5) * 8;  // first channel of this warp
+    const int *meta = bank.meta + o * 8;
+    const int Z = meta[META_ZEROS_C] + meta[META_ZEROS_T];
+    const int half = c0 / (RMNET_CV / 2);
+    const int n_splits = sched_ns ? __ldg(sched_ns + o) : n_splits_arg;  // KV chunks the persistent tcgen05 kernel used for this object
+    const unsigned ml_stride = (unsigned)n_obj_total * 2u * (unsigned)nq_pad;        // float2 units between splits
+    const unsigned op_stride = (unsigned)n_obj_total * RMNET_CV * (unsigned)nq_pad;  // floats between splits
+    const int pos = rect_pos(qrect, n, w);
+    const float2 *mlp = reinterpret_cast<const float2 *>(ml) + ((unsigned)o * 2u + half) * (unsigned)nq_pad + n;
+    const float *opb = opart + ((unsigned)o * RMNET_CV + (unsigned)cw) * (unsigned)nq_pad + n;
+    float *outp = mem_val + (unsigned)o * 2u * RMNET_CV * uN + (unsigned)cw * uN + pos;
+    // pass 1: the reference maximum over the splits (and 0 when masked cells exist: their score is exactly 0)
     float m_star = Z > 0 ? 0.f : -INFINITY;
+#pragma unroll 4
+    for (int s = 0; s < n_splits; ++s) m_star = fmaxf(m_star, ld_dep(mlp + (unsigned)s * ml_stride).x);
+    // pass 2: split weights, normaliser, weighted numerators.  A split that saw no cells (m = -inf) left its numerators
+    // unwritten: what was loaded for it is replaced by zero, not multiplied by it.
+    float Lsum = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
+    float num[8];
 #pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; ++s) m_star = fmaxf(m_star, st[s].x);
-    float L = Z > 0 ? (float)Z * ex2f(-m_star) : 0.f;
+    for (int k = 0; k < 8; ++k) num[k] = 0.f;
+#pragma unroll 4
+    for (int s = 0; s < n_splits; ++s) {
+      const float2 st = ld_dep(mlp + (unsigned)s * ml_stride);
+      const float *qp = opb + (unsigned)s * op_stride;
+      float v[8];
 #pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; ++s) {
-      wgt[s] = (st[s].x == -INFINITY) ? 0.f : ex2f(st[s].x - m_star);
-      L = fmaf(st[s].y, wgt[s], L);
+      for (int k = 0; k < 8; ++k) v[k] = ld_dep(qp + (unsigned)k * (unsigned)nq_pad);
+      const float wgt = (st.x == -INFINITY) ? 0.f : ex2f(st.x - m_star);
+      Lsum = fmaf(st.y, wgt, Lsum);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) num[k] = fmaf(wgt != 0.f ? v[k] : 0.f, wgt, num[k]);
     }
-    const float inv_l = 1.0f / L;
+    const float inv_l = 1.0f / Lsum;
 #pragma unroll
-    for (int s = 0; s < READ_MAX_SPLITS; ++s) wgt[s] *= inv_l;  // fold the normalisation into the split weights
-  }
-  float num[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) num[k] = 0.f;
-#pragma unroll
-  for (int u = 0; u < 8; ++u)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) num[k] = fmaf(wgt[u] != 0.f ? v[u][k] : 0.f, wgt[u], num[k]);
-  if (n_splits > 8) {
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float *q = opb + (unsigned)(8 + u) * op_stride;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[u][k] = (wgt[8 + u] != 0.f) ? ld_dep(q + (unsigned)k * (unsigned)nq_pad) : 0.f;
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u)
-#pragma unroll
-      for (int k = 0; k < 8; ++k) num[k] = fmaf(v[u][k], wgt[8 + u], num[k]);
-  }
-  if (live) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) outp[(unsigned)k * uN] = num[k];
+    for (int k = 0; k < 8; ++k) outp[(unsigned)k * uN] = num[k] * inv_l;
   }
   DEV_STAMP_MAX(9);
 }
 
 }  // namespace
 
-// fill_uniform = false: the uniform rows have been written by the read kernel (memory_read_umma.cu), gather role only.
 int launch_merge(const BankView &bank, const int *q_rects, int n_obj, int h, int w, int n_splits, bool device_sched,
-                 const ReadWorkspace &W, float *mem_val, bool fill_uniform, bool pdl, cudaStream_t st) {
+                 const ReadWorkspace &W, float *mem_val, bool pdl, cudaStream_t st) {
   const int N = h * w;
   const bool vec = N % 4 == 0 && ((uintptr_t)mem_val % 16 == 0);
   const int *ns = device_sched ? W.sched : nullptr;
-  const int n_gather_tiles = W.nq_pad / kQueriesPerCta;
-  if (vec) {
-    dim3 grid(n_gather_tiles + (fill_uniform ? cdiv(N, 128) : 0), RMNET_CV / kChPerCta, n_obj);
-    RMNET_CUDA(launch_kernel(merge_kernel<4>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, n_obj, n_splits, ns,
-                             W.opart, W.ml, W.nq_pad, mem_val, n_gather_tiles));
-  } else {
-    dim3 grid(n_gather_tiles + (fill_uniform ? cdiv(N, 128) : 0), RMNET_CV / kChPerCta, n_obj);
-    RMNET_CUDA(launch_kernel(merge_kernel<1>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, n_obj, n_splits, ns,
-                             W.opart, W.ml, W.nq_pad, mem_val, n_gather_tiles));
+  static int n_sms = 0;
+  if (n_sms == 0) {
+    int dev = 0, v = 0;
+    n_sms = (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
   }
-  RMNET_LAUNCH_CHECK();
+  // one launch per batch of at most SCHED_MAX_OBJ objects (the work list's tables); persistent grid: 8 CTAs per SM
+  for (int o0 = 0; o0 < n_obj; o0 += SCHED_MAX_OBJ) {
+    const int nb = n_obj - o0 < SCHED_MAX_OBJ ? n_obj - o0 : SCHED_MAX_OBJ;
+    const long long max_items = (long long)nb * (RMNET_CV / kChPerCta) * (cdiv(N, kQueriesPerCta) > cdiv(N, 128) ? cdiv(N, kQueriesPerCta) : cdiv(N, 128));
+    const long long cap = 8LL * n_sms;
+    dim3 grid((unsigned)(max_items < cap ? max_items : cap));
+    if (vec)
+      RMNET_CUDA(launch_kernel(merge_kernel<4>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, nb, o0, n_obj, n_splits, ns,
+                               W.opart, W.ml, W.nq_pad, mem_val));
+    else
+      RMNET_CUDA(launch_kernel(merge_kernel<1>, grid, dim3(kMergeThreads), 0, st, pdl, bank, q_rects, h, w, nb, o0, n_obj, n_splits, ns,
+                               W.opart, W.ml, W.nq_pad, mem_val));
+    RMNET_LAUNCH_CHECK();
+  }
   return RMNET_OK;
 }
 

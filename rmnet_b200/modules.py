@@ -94,7 +94,8 @@ class RegionalMemory:
         # region-kernel workspace of step(): zero-filled once, left zeroed by every launch (self-cleaning); owned by the
         # clip (not by the stream) so that a captured step and an eager step share it
         with torch.cuda.device(self.bank.device):
-            self._box_ws = torch.zeros(4096, dtype=torch.uint8, device=self.bank.device)
+            self._box_ws = torch.zeros(max(4096, ops.lib().rmnet_reg_att_map_workspace_bytes(1, 64)), dtype=torch.uint8,
+                                       device=self.bank.device)
 
     def memorize(self, k4, v4, masks, commit):
         """k4 [n,128,h,w], v4 [n,512,h,w]: kv_memory outputs (models/rmnet.py:236); masks [1,K,H,W]: the UNPADDED soft

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
 def test_abi_version_and_sizes():
     L = rmnet_b200.lib()
     assert L.rmnet_abi_version() == 1
-    assert L.rmnet_reg_att_map_workspace_bytes(1, 11) == 2 * 12 * 8 * 4   # two accumulator sets (warped, direct)
+    assert L.rmnet_reg_att_map_workspace_bytes(1, 11) == 16 * 2 * 12 * 8 * 4   # 16 copies of two accumulator sets (warped, direct)
     b1, b2 = L.rmnet_bank_bytes(3, 8128), L.rmnet_bank_bytes(3, 2 * 8128)
     assert b1 > 3 * 8128 * 640 * 4 and b2 > b1
     assert L.rmnet_bank_bytes(0, 64) == 0

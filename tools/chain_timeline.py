@@ -9,7 +9,7 @@ L.rmnet_debug_set_chain_stamps.argtypes = [ctypes.c_void_p]; L.rmnet_debug_set_c
 dev = torch.device("cuda:0")
 NAMES = ["regions start", "regions end", "pack start", "pack after wait", "pack end", "read start", "read end", "merge start",
          "merge gather after wait", "merge gather end", "merge fill end", "plan role end (pack kernel)", "plan role start", "plan: counts known", "plan: planners done"]
-MIN_SLOTS = (0, 2, 3, 5, 7, 8)
+MIN_SLOTS = (0, 2, 3, 5, 7, 8, 37)
 for wlname in sys.argv[1:] or ("c2", "c3"):
     wl = bench.WORKLOADS[wlname]; n, T, H, W = wl["n"], wl["T"], wl["H"], wl["W"]
     pool = bench.make_pool(wl, 1234, 2)
@@ -21,7 +21,7 @@ for wlname in sys.argv[1:] or ("c2", "c3"):
     step = lambda: rm.step(d["k4"], d["v4"], d["mask"][None], d["flow"][None], d["qk"], d["qv"], commit=False)
     for _ in range(3): step()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    init = torch.zeros(32, dtype=torch.int64); init[list(MIN_SLOTS)] = 2 ** 62
+    init = torch.zeros(40, dtype=torch.int64); init[list(MIN_SLOTS)] = 2 ** 62
     rows = []
     for rep in range(12):
         st = init.to(dev)
@@ -36,5 +36,6 @@ for wlname in sys.argv[1:] or ("c2", "c3"):
     r = np.median(np.array(rows[2:]), axis=0)
     print(f"== {wlname}: step by CUDA events {r[15]:.1f} us")
     for i, nm in enumerate(NAMES): print(f"   {nm:26s} {r[i]:8.2f} us")
+    print("   regions: first CTA leaves the pixel loop %.2f us, last CTA %.2f us, last ticket taken %.2f us" % tuple((raw[i] - raw[0]) / 1e3 for i in (37, 36, 38)))
     print(f"   plan: deal done {(raw[15] - raw[0]) / 1e3:.2f} us (cost {raw[19]}); fill margins done at", [round((raw[16 + m] - raw[0]) / 1e3, 2) for m in range(4)],
           "records", [int(raw[20 + m]) for m in range(4)], "cycles", [int(raw[24 + m]) for m in range(4)], "cost", [int(raw[28 + m]) for m in range(4)])
