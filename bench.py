@@ -774,7 +774,9 @@ def run_gpu(args, wl, rank, world, local_rank):
             "in_region_fraction": float(np.mean([c / (T * N) for c in cells])), "share_of_step": k_ms / (dev_ms / args.steps)}
     try:   # DRAM traffic per launch of the same kernel from the committed `ncu --set full` capture, when present
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        roof["traffic"] = tr.get(args.workload, {}).get("dram_bytes_per_launch")
+        key = args.workload if args.precision == "split3" else f"{args.workload}_{args.precision}"   # (captures exist for the strict mode)
+        roof["traffic"] = tr.get(key, {}).get("dram_bytes_per_launch")
+        roof["traffic_source"] = f"profiles/traffic.json[{key}] <- {tr.get(key, {}).get('report')}" if key in tr else None
     except (OSError, ValueError):
         pass
 

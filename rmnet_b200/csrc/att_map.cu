@@ -450,34 +450,47 @@ frame_boxes_kernel(const float *__restrict__ prev_mask, const float *__restrict_
     // trip for the whole array), a half-warp shuffle reduction folds them, the copy-0 lane finalises the channel
     static_assert(kWsCopies == 16 && kThreads % kWsCopies == 0, "half-warp fold");
     const int n_e = (DIRECT ? 2 : 1) * K;
-    for (int e0 = 0; e0 < n_e; e0 += kThreads / kWsCopies) {
-      const int e = e0 + threadIdx.x / kWsCopies, c = threadIdx.x % kWsCopies;
-      const bool act = e < n_e;
-      const int set = act ? e / K : 0, i = act ? e - set * K : 0;
-      int v[5] = {0, 0, 0, 0, 0};
-      if (act && i >= 1) {
-        // every publisher fenced before it took its ticket and ours was the last: plain (L2) loads see the final values
-        // and plain stores may clear them -- 5 atomic exchanges per word made this fold a 3 us tail of its own
-        int *w = ws_b + c * copy_stride + (set * (K + 1) + i) * kWsIntsPerChannel;
-        const int4 lo = ld_dep(reinterpret_cast<const int4 *>(w));
-        v[4] = ld_dep(w + 4);
-        v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
-        if (v[0] != 0) {  // (a copy that saw no hit is still all zero)
-          *reinterpret_cast<int4 *>(w) = make_int4(0, 0, 0, 0);
-          w[4] = 0;
+    constexpr int kPerPass = kThreads / kWsCopies, kBatch = 4;  // 16 channels per pass, the loads of 4 passes in one round trip
+    const int c = threadIdx.x % kWsCopies;
+    for (int e0 = 0; e0 < n_e; e0 += kPerPass * kBatch) {
+      int v[kBatch][5];
+#pragma unroll
+      for (int p = 0; p < kBatch; ++p) {
+        const int e = e0 + p * kPerPass + threadIdx.x / kWsCopies;
+        const int set = e / K, i = e - set * K;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) v[p][u] = 0;
+        if (e < n_e && i >= 1) {
+          // every publisher fenced before it took its ticket and ours was the last: plain (L2) loads see the final
+          // values and plain stores may clear them -- 5 atomic exchanges per word made this fold a 3 us tail of its own
+          int *w = ws_b + c * copy_stride + (set * (K + 1) + i) * kWsIntsPerChannel;
+          const int4 lo = ld_dep(reinterpret_cast<const int4 *>(w));
+          v[p][4] = ld_dep(w + 4);
+          v[p][0] = lo.x; v[p][1] = lo.y; v[p][2] = lo.z; v[p][3] = lo.w;
         }
       }
 #pragma unroll
-      for (int d = kWsCopies / 2; d >= 1; d >>= 1) {
-        v[0] += __shfl_xor_sync(0xffffffffu, v[0], d);
+      for (int p = 0; p < kBatch; ++p) {
+        const int e = e0 + p * kPerPass + threadIdx.x / kWsCopies;
+        const bool act = e < n_e;
+        const int set = act ? e / K : 0, i = act ? e - set * K : 0;
+        if (act && i >= 1 && v[p][0] != 0) {  // (a copy that saw no hit is still all zero)
+          int *w = ws_b + c * copy_stride + (set * (K + 1) + i) * kWsIntsPerChannel;
+          *reinterpret_cast<int4 *>(w) = make_int4(0, 0, 0, 0);
+          w[4] = 0;
+        }
 #pragma unroll
-        for (int u = 1; u < 5; ++u) v[u] = max(v[u], __shfl_xor_sync(0xffffffffu, v[u], d));
-      }
-      if (act && c == 0) {
-        int *bb = set ? bboxes_direct : bboxes_warp;
-        const BoxFinalize &f = set ? fin_direct : fin_warp;
-        if (i == 0) finalize_channel0(bb, (long long)b * K, f);
-        else finalize_values(v[0], v[1], v[2], v[3], v[4], bb, (long long)b * K + i, f);
+        for (int d = kWsCopies / 2; d >= 1; d >>= 1) {
+          v[p][0] += __shfl_xor_sync(0xffffffffu, v[p][0], d);
+#pragma unroll
+          for (int u = 1; u < 5; ++u) v[p][u] = max(v[p][u], __shfl_xor_sync(0xffffffffu, v[p][u], d));
+        }
+        if (act && c == 0) {
+          int *bb = set ? bboxes_direct : bboxes_warp;
+          const BoxFinalize &f = set ? fin_direct : fin_warp;
+          if (i == 0) finalize_channel0(bb, (long long)b * K, f);
+          else finalize_values(v[p][0], v[p][1], v[p][2], v[p][3], v[p][4], bb, (long long)b * K + i, f);
+        }
       }
     }
     if (threadIdx.x == 0) atomicExch(ws_b + K * kWsIntsPerChannel, 0);

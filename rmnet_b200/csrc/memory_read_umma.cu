@@ -173,7 +173,7 @@ struct Barriers {
 };
 
 struct Piece {
-  int o, qtile, half, tile_begin, n_it, slot, count;
+  int o, qtile, half, tile_begin, n_it, slot, count, q_rows;
 };
 // The pieces of this CTA in execution order (the plan of sched.cuh, written by the launch before this one); every warp
 // role walks the same list.  The first PLAN_SMEM_PIECES entries are staged in shared memory.
@@ -188,7 +188,8 @@ struct PieceIter {
     p.o = v.x & 255;
     p.qtile = (v.x >> 8) & 255;
     p.half = (v.x >> 16) & 15;
-    p.slot = (int)((unsigned)v.x >> 20);
+    p.slot = (v.x >> 20) & 15;
+    p.q_rows = (int)((unsigned)v.x >> 24) + 1;  // rows beyond are padding of the query tile: computed, never stored
     p.tile_begin = v.y;
     p.n_it = v.z;
     p.count = v.w;
@@ -453,15 +454,19 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
           tc_wait_ld();
           TMEM_LD16(t_base + TM_O + c + 32, rb, 0);
           TMEM_LD16(t_base + TM_O + c + 48, rb, 16);
+          if (row < pc.q_rows) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(ra[j]);  // lanes run along queries: coalesced
+            for (int j = 0; j < 32; ++j) ob[(c + j) * nq_pad] = __uint_as_float(ra[j]);  // lanes run along queries: coalesced
+          }
           tc_wait_ld();
           if (c + 64 < CVH) {
             TMEM_LD16(t_base + TM_O + c + 64, ra, 0);
             TMEM_LD16(t_base + TM_O + c + 80, ra, 16);
           }
+          if (row < pc.q_rows) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) ob[(c + 32 + j) * nq_pad] = __uint_as_float(rb[j]);
+            for (int j = 0; j < 32; ++j) ob[(c + 32 + j) * nq_pad] = __uint_as_float(rb[j]);
+          }
         }
         if (tstamp && first_piece && row == 0) tstamp[6] = clock64();
         first_piece = false;

@@ -51,7 +51,7 @@ __host__ __device__ inline PlanCost plan_cost(int precision) {
 struct PlanRecord { int o_slot, t0, len, cta_begin, n_ctas, unit0, gw, pad; };  // o | slot << 8
 
 struct PlanSmem {
-  int nt[SCHED_MAX_OBJ], nqt[SCHED_MAX_OBJ], count[SCHED_MAX_OBJ];
+  int nt[SCHED_MAX_OBJ], nqt[SCHED_MAX_OBJ], count[SCHED_MAX_OBJ], qcells[SCHED_MAX_OBJ];
   int ns[PLAN_N_MARGINS + 1][SCHED_MAX_OBJ];  // [0] = deal, [1 + m] = fill with margin m
   int ibase[SCHED_MAX_OBJ + 1];               // deal: first item of object o
   PlanRecord rec[PLAN_N_MARGINS][PLAN_MAX_RECORDS];
@@ -279,8 +279,8 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
 // bank_meta: per-slot counters; q_rects: query cell rectangles (nullptr = dense); temp_rects: when non-null, the cell
 // rectangles that are being stored as the temporary frame by this very launch (their cell count replaces META_CELLS_T,
 // exactly as bank_pack_kernel derives it).  Outputs: ns_out[o] partial slots per object (for merge.cu), hdr[c] =
-// (number of pieces, first piece) of CTA c, pieces[] = (o | qt << 8 | half << 16 | slot << 20, first tile, tiles,
-// stored cells of the object).
+// (number of pieces, first piece) of CTA c, pieces[] = (o | qt << 8 | half << 16 | slot << 20 | (live query rows - 1) << 24,
+// first tile, tiles, stored cells of the object).
 __device__ __forceinline__ void plan_build(PlanSmem &S, const int *__restrict__ bank_meta, const int *__restrict__ q_rects,
                                            const int *__restrict__ temp_rects, int cap, int n_obj, int h, int w, int G,
                                            int precision, int *__restrict__ ns_out, int2 *__restrict__ hdr,
@@ -300,6 +300,7 @@ __device__ __forceinline__ void plan_build(PlanSmem &S, const int *__restrict__ 
     }
     S.count[o] = count;
     S.nt[o] = (count + KV_TILE - 1) / KV_TILE;
+    S.qcells[o] = rect_cells(qr);
     S.nqt[o] = (rect_cells(qr) + UMMA_QT - 1) / UMMA_QT;
   }
   __syncthreads();
@@ -334,7 +335,8 @@ __device__ __forceinline__ void plan_build(PlanSmem &S, const int *__restrict__ 
         const unsigned nqt = S.nqt[o], nt = S.nt[o], ns = S.ns[0][o];
         const unsigned q = r / nqt, qt = r - q * nqt, half = q & 1u, j = q >> 1;
         const unsigned t0 = (j * nt) / ns, t1 = ((j + 1u) * nt) / ns;  // balanced partition of the nt tiles into ns chunks
-        pieces[(size_t)c * stride + n] = make_int4((int)((unsigned)o | (qt << 8) | (half << 16) | (j << 20)), (int)t0, (int)(t1 - t0), S.count[o]);
+        const unsigned rows = (unsigned)min((int)UMMA_QT, S.qcells[o] - (int)qt * UMMA_QT);  // live query rows of this tile
+        pieces[(size_t)c * stride + n] = make_int4((int)((unsigned)o | (qt << 8) | (half << 16) | (j << 20) | ((rows - 1u) << 24)), (int)t0, (int)(t1 - t0), S.count[o]);
       }
       hdr[c] = make_int2(n, c * stride);
     } else {
@@ -349,7 +351,8 @@ __device__ __forceinline__ void plan_build(PlanSmem &S, const int *__restrict__ 
           const int o = r.o_slot & 255, slot = (r.o_slot >> 8) + (int)grp;
           const unsigned unit = (unsigned)r.unit0 + (d - grp * (unsigned)r.gw), nqt = S.nqt[o];
           const unsigned half = unit / nqt, qt = unit - half * nqt;
-          pieces[(size_t)c * PLAN_FILL_STRIDE + n] = make_int4((int)((unsigned)o | (qt << 8) | (half << 16) | ((unsigned)slot << 20)), r.t0 + (int)grp * r.len, r.len, S.count[o]);
+          const unsigned rows = (unsigned)min((int)UMMA_QT, S.qcells[o] - (int)qt * UMMA_QT);
+          pieces[(size_t)c * PLAN_FILL_STRIDE + n] = make_int4((int)((unsigned)o | (qt << 8) | (half << 16) | ((unsigned)slot << 20) | ((rows - 1u) << 24)), r.t0 + (int)grp * r.len, r.len, S.count[o]);
           ++n;
         }
       }

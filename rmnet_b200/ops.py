@@ -303,7 +303,7 @@ class MemoryBank:
         lists = []
         for c in range(n_ctas.value):
             n, off = int(hdr[c, 0]), int(hdr[c, 1])
-            lists.append([(int(v[0]) & 255, (int(v[0]) >> 8) & 255, (int(v[0]) >> 16) & 15, (int(v[0]) >> 20) & 0xfff,
+            lists.append([(int(v[0]) & 255, (int(v[0]) >> 8) & 255, (int(v[0]) >> 16) & 15, (int(v[0]) >> 20) & 0xf,
                            int(v[1]), int(v[2]), int(v[3])) for v in pcs[off:off + n]])
         return ns, lists
 
