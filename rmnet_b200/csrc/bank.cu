@@ -24,8 +24,19 @@ constexpr int kKRowStride = RMNET_CK + 4;            // ushorts; keeps 8-byte ro
 constexpr int kGroups = kPackThreads / kCellsPerCta; // 4 channel groups; lanes run along cells (coalesced gathers)
 constexpr int kPerThread = kChunk / kGroups;         // 32 channels per thread
 
-// CTA roles (blockIdx.y + role_base): the memory side of models/rmnet.py:239-248 and the query side of :355-358, :163
+// CTA roles: the memory side of models/rmnet.py:239-248 and the query side of :355-358, :163
 enum { ROLE_MEM_KEYS = 0, ROLE_MEM_VALS = 1 /* ..4 */, ROLE_Q_KEYS = 5, ROLE_Q_PASS = 6 /* ..9 */, ROLE_PLAN = 10 /* one CTA: sched.cuh */ };
+// The grid is (cell tiles, objects, roles) with the roles SLOWEST and in the order the step needs them: CTAs are dispatched
+// in index order and only four fit an SM, so with the objects slowest (rounds 1-2a) the last objects' memory roles started
+// a wave late (the last object's memory values ended the pack stage); now the plan CTA is the very first one, then the
+// memory roles of ALL objects (the slowest: gather + split + scattered 2-byte stores + value sums), the query keys, and
+// the bandwidth-bound q_val passthrough last.
+enum { PACK_MEMORIZE = 0 /* memory roles */, PACK_FRAME = 1 /* plan + memory + query roles */, PACK_QUERY = 2 /* plan + query roles */ };
+__device__ __forceinline__ int pack_role(int kind, int z) {
+  if (kind == PACK_MEMORIZE) return z < 4 ? ROLE_MEM_VALS + z : ROLE_MEM_KEYS;
+  if (kind == PACK_QUERY) return z == 0 ? ROLE_PLAN : (z == 1 ? ROLE_Q_KEYS : ROLE_Q_PASS + (z - 2));
+  return z == 0 ? ROLE_PLAN : (z <= 4 ? ROLE_MEM_VALS + (z - 1) : (z == 5 ? ROLE_MEM_KEYS : (z == 6 ? ROLE_Q_KEYS : ROLE_Q_PASS + (z - 7))));
+}
 
 struct PackSmem {
   __align__(16) uint16_t hi[kCellsPerCta][kKRowStride];
@@ -88,22 +99,22 @@ template <int FMT>
 __global__ void __launch_bounds__(kPackThreads)
 bank_pack_kernel(BankView bank, const float *__restrict__ k4, long long k_obj_stride, long long k_ch_stride,
                  const float *__restrict__ v4, long long v_obj_stride, long long v_ch_stride,
-                 const int *__restrict__ rects, QuerySide qs, int role_base, int h, int w) {
+                 const int *__restrict__ rects, QuerySide qs, int kind, int h, int w) {
   __shared__ PackSmem sm;
   DEV_STAMP_MIN(2);
+  const int o = blockIdx.y;
+  const int role = pack_role(kind, (int)blockIdx.z);
+  if (role == ROLE_PLAN && (blockIdx.x != 0 || o != 0 || !qs.plan_hdr)) return;  // the plan is ONE CTA (the first of the grid)
   pdl_wait();     // chained launch: the rectangles come from the region kernel right before us
   pdl_trigger();  // (after the wait: the successor's prologue may then rely on everything before this kernel)
   DEV_STAMP_MIN(3);
-  const int o = blockIdx.z;
-  const int role = blockIdx.y + role_base;
   const int N = h * w;
 
   if (role == ROLE_PLAN) {
     // ---- work plan of the tcgen05 read that follows this launch (one CTA; sched.cuh).  With memory roles in the launch
     //      the temporary frame's cell counts come from `rects`, exactly as the memory roles below derive them.
-    if (blockIdx.x != 0 || o != 0 || !qs.plan_hdr) return;
-    plan_build(*reinterpret_cast<PlanSmem *>(&sm), qs.plan_bank_meta, qs.q_rects, role_base == ROLE_MEM_KEYS ? rects : nullptr,
-               qs.plan_cap_cells, (int)gridDim.z, h, w, qs.plan_ctas, qs.plan_precision, qs.plan_ns,
+    plan_build(*reinterpret_cast<PlanSmem *>(&sm), qs.plan_bank_meta, qs.q_rects, kind == PACK_FRAME ? rects : nullptr,
+               qs.plan_cap_cells, (int)gridDim.y, h, w, qs.plan_ctas, qs.plan_precision, qs.plan_ns,
                reinterpret_cast<int2 *>(qs.plan_hdr), reinterpret_cast<int4 *>(qs.plan_pieces), qs.plan_piece_cap);
     DEV_STAMP_MAX(11);
     return;
@@ -260,13 +271,13 @@ using namespace rmnet;
 // Query side alone (standalone rmnet_bank_memory_read): roles 5..9 of the pack kernel.
 int rmnet::launch_query_side(const QuerySide &qs, int n_obj, int h, int w, int elem_format, cudaStream_t st) {
   BankView none = {};
-  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), qs.plan_hdr ? 6 : 5, n_obj);
+  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), n_obj, 6);
   if (elem_format == 0)
     RMNET_CUDA(launch_kernel(bank_pack_kernel<0>, grid, dim3(kPackThreads), 0, st, false, none, (const float *)nullptr, 0LL, 0LL,
-                             (const float *)nullptr, 0LL, 0LL, (const int *)nullptr, qs, (int)ROLE_Q_KEYS, h, w));
+                             (const float *)nullptr, 0LL, 0LL, (const int *)nullptr, qs, (int)PACK_QUERY, h, w));
   else
     RMNET_CUDA(launch_kernel(bank_pack_kernel<1>, grid, dim3(kPackThreads), 0, st, false, none, (const float *)nullptr, 0LL, 0LL,
-                             (const float *)nullptr, 0LL, 0LL, (const int *)nullptr, qs, (int)ROLE_Q_KEYS, h, w));
+                             (const float *)nullptr, 0LL, 0LL, (const int *)nullptr, qs, (int)PACK_QUERY, h, w));
   RMNET_LAUNCH_CHECK();
   return RMNET_OK;
 }
@@ -318,13 +329,14 @@ int rmnet::bank_memorize_impl(void *bank, size_t bank_bytes, int n_slots, int ca
   // with a query side (rmnet_frame_step) the same launch also packs the query keys and writes the q_val passthrough
   QuerySide qs = {};
   if (query_side) qs = *query_side;
-  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), query_side ? (qs.plan_hdr ? 11 : 10) : 5, n_obj);
+  dim3 grid(cdiv(cdiv(h * w, 128) * 128, kCellsPerCta), n_obj, query_side ? 11 : 5);
+  const int kind = query_side ? PACK_FRAME : PACK_MEMORIZE;
   if (elem_format == 0)
     RMNET_CUDA(launch_kernel(bank_pack_kernel<0>, grid, dim3(kPackThreads), 0, st, chained, bv, k4, k_obj_stride, k_ch_stride, v4,
-                             v_obj_stride, v_ch_stride, rects, qs, 0, h, w));
+                             v_obj_stride, v_ch_stride, rects, qs, kind, h, w));
   else
     RMNET_CUDA(launch_kernel(bank_pack_kernel<1>, grid, dim3(kPackThreads), 0, st, chained, bv, k4, k_obj_stride, k_ch_stride, v4,
-                             v_obj_stride, v_ch_stride, rects, qs, 0, h, w));
+                             v_obj_stride, v_ch_stride, rects, qs, kind, h, w));
   RMNET_LAUNCH_CHECK();
   if (commit) {
     RMNET_CUDA(launch_kernel(bank_commit_kernel, dim3(n_obj), dim3(128), 0, st, chained, bv, n_obj));

@@ -54,7 +54,7 @@ struct PlanSmem {
   int nt[SCHED_MAX_OBJ], nqt[SCHED_MAX_OBJ], count[SCHED_MAX_OBJ], qcells[SCHED_MAX_OBJ];
   int ns[PLAN_N_MARGINS + 1][SCHED_MAX_OBJ];  // [0] = deal, [1 + m] = fill with margin m
   int ibase[SCHED_MAX_OBJ + 1];               // deal: first item of object o
-  PlanRecord rec[PLAN_N_MARGINS][PLAN_MAX_RECORDS];
+  alignas(16) PlanRecord rec[PLAN_N_MARGINS][PLAN_MAX_RECORDS];
   int nrec[PLAN_N_MARGINS];
   unsigned cost[PLAN_N_MARGINS + 1];          // estimated makespan in cycles (0xffffffff = not applicable)
   int deal_items, winner;
@@ -66,6 +66,14 @@ __device__ __forceinline__ unsigned plan_ceil_div(unsigned a, unsigned b, float 
   q += (q * b < a) ? 1u : 0u;
   q += (q * b < a) ? 1u : 0u;
   q -= (q > 0 && (q - 1u) * b >= a) ? 1u : 0u;
+  return q;
+}
+
+// floor(a / b) for 0 <= a < 2^20, 0 < b < 2^20 (one float multiply and two fix-ups)
+__device__ __forceinline__ int plan_floor_div(int a, int b) {
+  int q = (int)((float)a * __frcp_rn((float)b));
+  q -= (q * b > a) ? 1 : 0;
+  q += ((q + 1) * b <= a) ? 1 : 0;
   return q;
 }
 
@@ -169,9 +177,12 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
       int rem = S.nt[o], slot = 0, t0 = 0;
       while (rem > 0) {
         if (++steps > PLAN_MAX_STEPS) { ok = false; break; }
-        // pass 1: the g least-loaded CTAs (whole segments in ascending load; the last one may be split)
+        // pass 1: the g least-loaded CTAs (whole segments in ascending load; the last one may be split).  The plan CTA
+        // shares its SM's issue slots with three pack CTAs, so what counts here is the instruction count: the common
+        // case -- the least-loaded segment alone has g CTAs -- needs one REDUX and two shuffles per step.
         unsigned long long taken = 0ull;
         int need = g, base = 0, last_seg = 0, last_k = 0, first_len = 0;
+        unsigned first_meta = 0u;
         while (need > 0) {
           unsigned k0 = 0xffffffffu;
 #pragma unroll
@@ -183,9 +194,10 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
           if (k0 == 0xffffffffu) { ok = false; break; }
           const int i = (int)(k0 & 63u);
           const unsigned ma = __shfl_sync(0xffffffffu, smeta[0], i & 31), mb = __shfl_sync(0xffffffffu, smeta[1], i & 31);
-          const int len_i = (int)((((i >> 5) ? mb : ma) >> 10) & 1023u);
+          const unsigned mi = (i >> 5) ? mb : ma;
+          const int len_i = (int)((mi >> 10) & 1023u);
           const int k = min(need, len_i);
-          if (need == g) first_len = len_i;
+          if (need == g) { first_len = len_i; first_meta = mi; }
           taken |= 1ull << i;
           need -= k;
           base = (int)(k0 >> 6);
@@ -193,6 +205,7 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
           last_k = k;
         }
         if (!ok) break;
+        const bool single = first_len >= g;  // the first pick covered the whole group
         // chunk length: up to the level, within the chain bound, leaving neither a tiny tail nor more than the
         // remaining partial slots can take
         const int avail = Lv - base - (base == 0 ? C.first : C.extra);
@@ -212,7 +225,7 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
           // The next chunks of this object would take the next g CTAs of the same segment (same load, same room) and get
           // the same length as long as none of the rules above modifies it: place them all in this step.
           if (ln == ln0 && first_len >= 2 * g) {
-            nb = min(min(first_len / g, slots_left - 1), rem / ln);
+            nb = min(min(plan_floor_div(first_len, g), slots_left - 1), plan_floor_div(rem, ln));
             for (; nb >= 2; --nb) {  // the rules as chunk number nb - 1 would see them
               const int rem_j = rem - (nb - 1) * ln, left_j = slots_left - (nb - 1), tail_j = rem_j - ln;
               if (left_j >= 2 && rem_j - MAX_TILES_PER_SPLIT * (left_j - 1) <= ln && (tail_j == 0 || tail_j >= PLAN_MIN_CHUNK)) break;
@@ -223,26 +236,18 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
         }
         // pass 2: records + segment updates
         int unit = 0;
-        unsigned long long tm = taken;
-        while (tm) {
-          const int i = __ffsll((long long)tm) - 1;
-          tm &= tm - 1ull;
+        auto place = [&](int i, int ld, unsigned mt) {  // segment i (load ld, meta mt) gives its first k CTAs to this chunk
           const int src = i & 31, hi = i >> 5;
-          const int l0 = __shfl_sync(0xffffffffu, sload[0], src), l1 = __shfl_sync(0xffffffffu, sload[1], src);
-          const unsigned m0 = __shfl_sync(0xffffffffu, smeta[0], src), m1 = __shfl_sync(0xffffffffu, smeta[1], src);
-          const int ld = hi ? l1 : l0;
-          const unsigned mt = hi ? m1 : m0;
           const int bg = (int)(mt & 1023u), sl = (int)((mt >> 10) & 1023u), np = (int)(mt >> 20) + 1;
           const int k = (i == last_seg) ? last_k : sl;
           const int nl = ld + (ld == 0 ? C.first : C.extra) + ln * C.tile;
           maxload = max(maxload, nl);
           max_np = max(max_np, np);
-          if (nrec >= PLAN_MAX_RECORDS || (k < sl && nseg >= PLAN_MAX_SEGS) || nl >= (1 << 25) || np > PLAN_FILL_STRIDE) { ok = false; break; }
+          if (nrec >= PLAN_MAX_RECORDS || (k < sl && nseg >= PLAN_MAX_SEGS) || nl >= (1 << 25) || np > PLAN_FILL_STRIDE) { ok = false; return; }
           if (lane == 0) {
-            PlanRecord r;
-            r.o_slot = o | (slot << 8); r.t0 = t0; r.len = ln; r.cta_begin = bg; r.n_ctas = k; r.unit0 = unit;
-            r.gw = nb > 1 ? g : k; r.pad = 0;
-            rec[nrec] = r;
+            int4 *r = reinterpret_cast<int4 *>(&rec[nrec]);
+            r[0] = make_int4(o | (slot << 8), t0, ln, bg);
+            r[1] = make_int4(k, unit, nb > 1 ? g : k, 0);
           }
           const unsigned taken_meta = (unsigned)bg | ((unsigned)k << 10) | ((unsigned)np << 20);
           if (k == sl) {  // the whole segment moves up
@@ -254,6 +259,19 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
           }
           ++nrec;
           unit += k;
+        };
+        if (single) {
+          place(last_seg, base, first_meta);
+        } else {
+          unsigned long long tm = taken;
+          while (tm && ok) {
+            const int i = __ffsll((long long)tm) - 1;
+            tm &= tm - 1ull;
+            const int src = i & 31;
+            const int l0 = __shfl_sync(0xffffffffu, sload[0], src), l1 = __shfl_sync(0xffffffffu, sload[1], src);
+            const unsigned m0 = __shfl_sync(0xffffffffu, smeta[0], src), m1 = __shfl_sync(0xffffffffu, smeta[1], src);
+            place(i, (i >> 5) ? l1 : l0, (i >> 5) ? m1 : m0);
+          }
         }
         if (!ok) break;
         rem -= ln * nb; t0 += ln * nb; slot += nb;
