@@ -188,7 +188,10 @@ RMNET_API int rmnet_bank_stats_host(const void *bank, int n_slots, int cap_cells
  *   stages: RMNET_STAGE_ALL normally; RMNET_STAGE_QUERY / _PARTIAL / _MERGE run only the query-side preparation
  *     (k4e*att16 packed for the tensor cores, v4e*att16 into mem_val[:,512:]) / the split-KV attention kernel / the
  *     merge+scatter kernel, each of which needs its predecessors' results from an earlier call with the same arguments
- *     (so a benchmark can time each launch alone).
+ *     (so a benchmark can time each launch alone).  The query stage also builds, on the device, the work plan that the
+ *     tcgen05 attention kernel walks (which KV chunk of which object runs on which SM; rmnet_memory_read_plan_host
+ *     copies it out): a PARTIAL-only call relies on the plan of the last QUERY stage run on this workspace, so the bank
+ *     and q_rects must not have changed in between.
  * ------------------------------------------------------------------------------------------- */
 #define RMNET_STAGE_PARTIAL 1
 #define RMNET_STAGE_MERGE 2
