@@ -92,6 +92,15 @@ __device__ __forceinline__ uint4 ld_dep(const uint4 *p) {
   return v;
 }
 
+// The other way to keep such loads behind the wait, for hot loops that want ordinary (schedulable, `__ldg`) loads: pass the
+// base pointer through this AFTER pdl_wait().  The loads' addresses then depend on an asm volatile that is ordered after
+// the wait, so nothing derived from the returned pointer can be hoisted above it.
+template <typename T>
+__device__ __forceinline__ T *pdl_launder(T *p) {
+  asm volatile("" : "+l"(p) : : "memory");
+  return p;
+}
+
 bool pdl_enabled();  // runtime.cu: false when the environment sets RMNET_DISABLE_PDL=1 (debugging aid)
 
 template <typename... KArgs, typename... Args>

@@ -259,6 +259,7 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
   }
   if (tstamp && threadIdx.x == 32) tstamp[11] = clock64();
   pdl_wait();  // the plan, the packed queries and the temporary frame all come from the launch before this one
+  const uint16_t *const qhi_w = pdl_launder(qhi), *const qlo_w = pdl_launder(qlo);  // (common.cuh: loads stay behind the wait)
   if (warp == 3) {
     const int2 hd = ld_dep(plan_hdr + blockIdx.x);  // (everything the pack kernel wrote: ld_dep, common.cuh)
     if (lane == 0) s_hdr = hd;
@@ -303,6 +304,11 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     // ================= value-tile TMA producer =================
     if (lane == 0) {
       int vt = 0;
+      // At kernel start all 148 CTAs fill their rings and fetch their Q rows at once: 42 MB through L2 -> SM at its
+      // throughput cap, ~7 k cycles before the first score MMA could issue.  The first score tile needs Q and one key
+      // stage only, so the value ring (128 of the 224 KB) waits until this CTA's Q rows are in TMEM; its first tile is
+      // due a score MMA chain and a softmax pass (~2.3 k cycles) later.
+      mbar_wait(smem_u32(&bars->q_ready), 0);
       while (iter.next(pc)) {
         for (int it = 0; it < pc.n_it; ++it, ++vt) {
           const int s = vt % VST;
@@ -399,16 +405,16 @@ memory_read_umma_kernel(const __grid_constant__ CUtensorMap map_khi, const __gri
     uint32_t qh[RMNET_CK / 2], ql[USE_LO ? RMNET_CK / 2 : 1];
     auto fetch_q = [&](const Piece &p) {
       const size_t r = ((size_t)p.o * nq_pad + p.qtile * QT + (row & ~31)) * (RMNET_CK / 8) + (row & 31);  // uint4 units
-      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi) + r, *pl = reinterpret_cast<const uint4 *>(qlo) + r;
+      const uint4 *ph = reinterpret_cast<const uint4 *>(qhi_w) + r, *pl = reinterpret_cast<const uint4 *>(qlo_w) + r;
 #pragma unroll
       for (int j = 0; j < RMNET_CK / 8; ++j) {
-        const uint4 v = ld_dep(ph + j * 32);
+        const uint4 v = __ldg(ph + j * 32);
         qh[4 * j] = v.x; qh[4 * j + 1] = v.y; qh[4 * j + 2] = v.z; qh[4 * j + 3] = v.w;
       }
       if (USE_LO) {
 #pragma unroll
         for (int j = 0; j < RMNET_CK / 8; ++j) {
-          const uint4 v = ld_dep(pl + j * 32);
+          const uint4 v = __ldg(pl + j * 32);
           ql[4 * j] = v.x; ql[4 * j + 1] = v.y; ql[4 * j + 2] = v.z; ql[4 * j + 3] = v.w;
         }
       }
