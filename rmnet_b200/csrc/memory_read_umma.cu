@@ -1,7 +1,9 @@
 // memory_read_umma.cu -- the fused regional memory read on Blackwell tensor cores (sm_100a).
 //
-// One CTA = (128 in-region queries) x (one object) x (one half of the 512 value channels) x (one KV split).
-// It streams the object's region-compacted bank in tiles of 64 memory cells and keeps everything on chip:
+// A piece = (128 in-region queries) x (one object) x (one half of the 512 value channels) x (one KV chunk).  The
+// persistent grid (one CTA per SM) walks the work plan that the launch before this one built on the device from the actual
+// region sizes (sched.cuh: which chunk of which object on which SM, in which order); warp 3 stages the CTA's piece list.
+// A piece streams its chunk of the object's region-compacted bank in tiles of 64 memory cells and keeps everything on chip:
 //
 //   warp 0 : TMA producer for key tiles   (cp.async.bulk.tensor, SWIZZLE_128B, 3-stage mbarrier ring)
 //   warp 2 : TMA producer for value tiles (2-stage ring)
