@@ -96,7 +96,7 @@ int rmnet_has_umma(void) { return umma_supported(64) ? 1 : 0; }
 
 size_t rmnet_memory_read_workspace_bytes(int n_obj, int h, int w, int cap_cells) {
   if (n_obj <= 0 || h <= 0 || w <= 0 || cap_cells <= 0) return 0;
-  return read_workspace(nullptr, n_obj, h * w, READ_MAX_SPLITS).total;  // the stream-K kernel may cut a unit into that many pieces
+  return read_workspace(nullptr, n_obj, h * w, READ_MAX_SPLITS).total;  // the plan may cut an object into that many KV chunks (partial slots)
 }
 
 int rmnet_bank_memory_read(const void *bank, size_t bank_bytes, int n_slots, int cap_cells, const float *q_key,
