@@ -40,6 +40,8 @@ def test_abi_version_and_sizes():
     # split-KV partials: at least one [n_obj,512,nq_pad] f32 block per split; grows with the bank capacity
     w1, w2 = L.rmnet_memory_read_workspace_bytes(3, 30, 54, 8128), L.rmnet_memory_read_workspace_bytes(3, 30, 54, 32448)
     assert w1 >= 3 * 512 * 1664 * 4 and w2 >= w1
+    # ... plus the read kernel's work plan: a header per persistent CTA and the piece lists (16 bytes per piece)
+    assert w1 >= 16 * 3 * 512 * 1664 * 4 + 256 * 8 + 256 * 16 * 16
 
 
 def test_argument_validation_returns_error_codes_without_touching_the_gpu():
@@ -54,6 +56,14 @@ def test_argument_validation_returns_error_codes_without_touching_the_gpu():
     addr = (ctypes.addressof(buf) + 15) // 16 * 16
     assert L.rmnet_reg_att_map_forward(addr, 1, 1, 8, 8, 0.5, 10, 64, addr, None, addr, 4096, None) == -1
     assert L.rmnet_reg_att_map_forward(addr, 1, 11, 8, 8, 0.5, 10, 64, addr, None, addr, 8, None) == -3  # workspace too small
+    # the region workspace is 16 copies of two accumulator sets and must be 16-byte aligned
+    assert L.rmnet_reg_att_map_forward(addr, 1, 2, 8, 8, 0.5, 10, 64, addr, None, addr + 4, 4096, None) == -1
+    assert b"aligned" in L.rmnet_last_error()
+    # plan read-back: null pointers / bad sizes are rejected before any CUDA call
+    assert L.rmnet_memory_read_plan_host(None, 3, 30, 54, None, None, None, 16, None, None) == -1
+    n_ctas = ctypes.c_int(0)
+    assert L.rmnet_memory_read_plan_host(addr, 0, 30, 54, addr, addr, addr, 16, ctypes.byref(n_ctas), None) == -1
+    assert L.rmnet_memory_read_plan_host(addr, 65, 30, 54, addr, addr, addr, 16, ctypes.byref(n_ctas), None) == -1   # > 64 objects: no tcgen05 plan
 
 
 def test_wrappers_reject_cpu_tensors_like_the_reference_check_input():
