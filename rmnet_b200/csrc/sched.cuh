@@ -119,7 +119,8 @@ __device__ __forceinline__ void plan_deal(PlanSmem &S, int n_obj, int G, PlanCos
     int acc = 0;
     for (int o = 0; o < n_obj; ++o) {
       const int nt = S.nt[o];
-      const int ns = (nt > 0 && S.nqt[o] > 0) ? (nt + c - 1) / c : 0;
+      // (with a huge object in the bank c exceeds the chain bound: the other objects keep theirs as far as their 16 slots go)
+      const int ns = (nt > 0 && S.nqt[o] > 0) ? max((nt + c - 1) / c, min((int)READ_MAX_SPLITS, (nt + MAX_TILES_PER_SPLIT - 1) / MAX_TILES_PER_SPLIT)) : 0;
       S.ns[0][o] = ns;
       S.ibase[o] = acc;
       acc += ns * 2 * S.nqt[o];
@@ -234,6 +235,7 @@ __device__ __forceinline__ void plan_fill(PlanSmem &S, int m, int n_obj, int G, 
             if (nb > 1) last_k = g * nb;
           }
         }
+        if (ln > MAX_TILES_PER_SPLIT) { ok = false; break; }  // (slots ran out before the tiles did: the dealt plan handles it)
         // pass 2: records + segment updates
         int unit = 0;
         auto place = [&](int i, int ld, unsigned mt) {  // segment i (load ld, meta mt) gives its first k CTAs to this chunk

@@ -5,7 +5,9 @@ import numpy as np
 import pytest
 import torch
 
+import plan_model
 import rmnet_b200
+from plan_model import check_plan
 from rmnet_b200 import ops
 
 pytestmark = pytest.mark.gpu
@@ -28,42 +30,6 @@ def _random_rects(rng, n, h, w, lo, hi, p_empty=0.0):
 
 def _cells(r):
     return max(0, int(r[1]) - int(r[0]) + 1) * max(0, int(r[3]) - int(r[2]) + 1)
-
-
-def check_plan(ns, lists, counts, q_cells, strict_chain=True):
-    """counts[o] stored cells, q_cells[o] in-region query cells."""
-    n = len(counts)
-    cover = {}
-    for c, pcs in enumerate(lists):
-        for (o, qt, half, slot, t0, ln, cnt) in pcs:
-            assert 0 <= o < n and half in (0, 1) and ln > 0 and t0 >= 0
-            assert cnt == counts[o], "piece carries the object's stored-cell count"
-            assert slot < ns[o] <= 16
-            cover.setdefault((o, qt, half), []).append((t0, ln, slot, c))
-    for o in range(n):
-        nt = (counts[o] + 63) // 64
-        nqt = (q_cells[o] + 127) // 128
-        if nt == 0 or nqt == 0:
-            assert ns[o] == 0 and not any(k[0] == o for k in cover)
-            continue
-        chunks0 = None
-        for qt in range(nqt):
-            for half in (0, 1):
-                segs = sorted(cover.get((o, qt, half), []))
-                assert segs, f"object {o} tile {qt} half {half} has no pieces"
-                pos = 0
-                for (t0, ln, slot, c) in segs:
-                    assert t0 == pos, "KV tiles covered once, in order, without gaps"
-                    pos += ln
-                assert pos == nt
-                assert sorted(s[2] for s in segs) == list(range(ns[o])), "every partial slot written exactly once"
-                chunks = [(t0, ln, slot) for (t0, ln, slot, c) in segs]
-                if chunks0 is None:
-                    chunks0 = chunks
-                assert chunks == chunks0, "all query tiles / halves of an object share the chunking (slot <-> chunk)"
-                if strict_chain and nt <= 16 * 64:
-                    assert max(ln for _, ln, _ in chunks) <= 64, "accumulation-chain bound"
-        assert not any(k[0] == o and k[1] >= nqt for k in cover)
 
 
 CASES = [
@@ -98,11 +64,17 @@ def test_plan_covers_the_work_and_the_read_matches_the_ffma_kernel(case, prec):
     ns, lists = bank.read_plan(n)
     st = bank.stats()
     counts = [int(st[o, 0] + st[o, 1]) for o in range(n)]
-    check_plan(ns, lists, counts, [_cells(r) for r in q_rects])
+    q_cells = [_cells(r) for r in q_rects]
+    check_plan(ns, lists, counts, q_cells)
+    # the device-built plan against the plain-Python restatement of the planner (tests/plan_model.py), piece by piece
+    win, ns_model, lists_model = plan_model.build_plan(counts, q_cells, G=len(lists), precision=prec)
+    assert ns.tolist() == ns_model, f"partial slots per object: device {ns.tolist()}, model {ns_model} (planner {win})"
+    for c, (dev_pcs, mod_pcs) in enumerate(zip(lists, lists_model)):
+        assert [tuple(p) for p in dev_pcs] == [p[:7] for p in mod_pcs], f"CTA {c}: device {dev_pcs}, model {mod_pcs} (planner {win})"
     loads = [sum(p[5] for p in pcs) for pcs in lists]
     total = sum(loads)
     if total:
-        print(f"plan: {sum(1 for l in loads if l)} CTAs busy, tiles/CTA max {max(loads)} mean {total / len(loads):.1f}, "
+        print(f"plan (planner {win}): {sum(1 for l in loads if l)} CTAs busy, tiles/CTA max {max(loads)} mean {total / len(loads):.1f}, "
               f"pieces/CTA max {max(len(p) for p in lists)}, ns {ns.tolist()}")
     ref = bank.read(qk, qv, qr, n, precision=rmnet_b200.RMNET_PREC_SPLIT3, impl=rmnet_b200.RMNET_IMPL_SIMT)
     err = (got - ref).abs().max().item()
@@ -143,3 +115,39 @@ def test_plan_is_rebuilt_by_every_frame_step():
         for o in range(n):
             if counts[o] and ns[o]:
                 assert o in got_counts
+
+
+@pytest.mark.parametrize("prec", [rmnet_b200.RMNET_PREC_SPLIT3, rmnet_b200.RMNET_PREC_MIXED], ids=["split3", "mixed"])
+def test_device_plan_equals_the_model_on_random_states(prec):
+    """Many bank states, cheaply: the per-object cell counters of an (otherwise empty) bank are poked directly, the query
+    stage of the read (pack kernel: query roles + the plan role) is run alone, and the plan it leaves in the workspace is
+    compared piece by piece with tests/plan_model.py -- single-wave states (water-filling, with its multi-segment takes,
+    splits and bulk records), small ones (dealt) and one-object extremes."""
+    n_max, T, h, w = 10, 40, 30, 54
+    N = h * w
+    rng = np.random.default_rng(100 + prec)
+    bank = ops.MemoryBank(n_max, h, w, T, DEV)
+    off = bank.ptr - bank.blob.data_ptr()
+    meta = bank.blob[off:off + n_max * 32].view(torch.int32).view(n_max, 8)
+    qk = torch.randn((128, h, w), device=DEV)
+    qv = torch.randn((512, h, w), device=DEV)
+    wins = [0, 0, 0, 0]
+    for it in range(160):
+        n = int(rng.integers(1, n_max + 1))
+        t_eff = int(rng.integers(1, T + 1)) if it % 3 else int(rng.integers(1, 6))
+        counts = [0 if rng.uniform() < 0.08 else int(min(bank.cap, t_eff * N * rng.uniform(0.02, 1.0) * rng.uniform(0.1, 1.0))) for _ in range(n)]
+        q_rects = _random_rects(rng, n, h, w, 0.05, 1.0, p_empty=0.08)
+        m = torch.zeros((n_max, 8), dtype=torch.int32)
+        m[:n, 0] = torch.tensor(counts, dtype=torch.int32)
+        meta.copy_(m.to(DEV))
+        bank.read(qk, qv, torch.from_numpy(q_rects).to(DEV), n, precision=prec, impl=rmnet_b200.RMNET_IMPL_UMMA, stages=4)
+        ns, lists = bank.read_plan(n)
+        q_cells = [_cells(r) for r in q_rects]
+        win, ns_model, lists_model = plan_model.build_plan(counts, q_cells, G=len(lists), precision=prec)
+        wins[win] += 1
+        assert ns.tolist() == ns_model, f"state {it}: counts {counts} q {q_cells}: device ns {ns.tolist()}, model {ns_model} (planner {win})"
+        for c, (dev_pcs, mod_pcs) in enumerate(zip(lists, lists_model)):
+            assert [tuple(p) for p in dev_pcs] == [p[:7] for p in mod_pcs], f"state {it} CTA {c}: device {dev_pcs}, model {mod_pcs} (planner {win}; counts {counts}, q {q_cells})"
+        check_plan(ns, lists, counts, q_cells)
+    print("planner chosen (deal, fill 1.5, 2.25, 3.0 tiles):", wins)
+    assert sum(wins[1:]) >= 10, "the random states should exercise the water-filling planner"
