@@ -772,6 +772,14 @@ def run_gpu(args, wl, rank, world, local_rank):
             "passes": passes, "algorithmic_gflop": flops / 1e9, "algorithmic_mbytes": byts / 1e6,
             "hbm_achieved_gbs": byts / (k_ms * 1e-3) / 1e9, "hbm_frac": byts / (k_ms * 1e-3) / 1e9 / hbm_peak,
             "in_region_fraction": float(np.mean([c / (T * N) for c in cells])), "share_of_step": k_ms / (dev_ms / args.steps)}
+    try:   # the work plan the timed launches walked (built on the device, rmnet_b200/csrc/sched.cuh): a diagnostic, never fatal
+        ns_plan, lists = rm.bank.read_plan(n)
+        loads = [sum(p[5] for p in pcs) for pcs in lists]
+        roof["plan"] = {"ctas": len(lists), "ctas_busy": int(sum(1 for v in loads if v)), "kv_tiles_per_cta_max": int(max(loads)),
+                        "kv_tiles_per_cta_mean": float(sum(loads)) / max(len(loads), 1), "pieces_per_cta_max": int(max(len(p) for p in lists)),
+                        "kv_chunks_per_object": [int(v) for v in ns_plan]}
+    except Exception as e:  # noqa: BLE001
+        roof["plan"] = {"unavailable": repr(e)[:200]}
     try:   # DRAM traffic per launch of the same kernel from the committed `ncu --set full` capture, when present
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
         key = args.workload if args.precision == "split3" else f"{args.workload}_{args.precision}"   # (captures exist for the strict mode)
