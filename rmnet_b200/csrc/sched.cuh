@@ -12,8 +12,9 @@
 //             is made as long as fits under a target level Lv = ideal makespan + margin (<= 64 tiles: accumulation-chain
 //             bound, common.cuh), so CTAs end up level although group widths (2..2*nqt) and object sizes differ; the
 //             short remainders of one object fill the room that the others left.  Three margins are tried in parallel
-//             (one warp each).  At the headline size (480p, 5 objects, T = 20) the longest CTA drops from 43 tiles + 1
-//             piece to ~38 tiles in 1-2 pieces (-10 % kernel time); tools/sched_model.py is the offline model.
+//             (one warp each).  At the headline size (480p, 5 objects, T = 20) the longest CTA drops from 43 tiles in 1
+//             piece to 37 tiles in 1-2 pieces (kernel 88 -> 75 us).  tests/plan_model.py restates both planners in plain
+//             Python; the GPU tests hold the device-built plan equal to it piece by piece (tests/test_gpu_plan.py).
 //
 // Cost model (cycles, measured with the DEV stamps: tools/umma_timeline.py): a KV tile, the first piece's prologue +
 // drain, every further piece's restart.
@@ -25,7 +26,7 @@ namespace rmnet {
 enum {
   PLAN_MAX_RECORDS = 160,    // group records of one water-filling run
   PLAN_MAX_SEGS = 64,        // CTA ranges of equal load
-  PLAN_MAX_STEPS = 72,       // chunks placed by one water-filling run (bounds its latency: ~150 cycles each)
+  PLAN_MAX_STEPS = 72,       // placement steps of one water-filling run (bounds its latency: ~1 200 cycles each on a shared SM)
   PLAN_FILL_STRIDE = 16,     // piece-list capacity per CTA of a water-filling plan
   PLAN_MIN_CHUNK = 4,        // tiles
   PLAN_FILL_MAX_LOAD = 96,   // water-filling only when the ideal load is at most this many tiles per CTA ...
